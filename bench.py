@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the MAPF hot path (step + observe) on B200, next to the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one joint step (mapf_step) + one observation build (mapf_observe) over all worlds of the rank:
+the rollout loop's per-step env work (runner.py:64-100) with the policy excluded.
+Workload (N=1) = BASELINE.json configs[2]: 65 536 lockstep 40x40 worlds, 32 agents, obstacle density U[0,0.3],
+uniform random actions.  Weak scaling: every rank owns 65 536 worlds; worlds never communicate.
+
+Printed JSON (rank 0): value = whole-job agent-steps/s with inputs resident in HBM; `e2e` = the same through the
+host-buffer C-ABI call (actions from pinned host memory, per-agent results read back to the host every step);
+`roofline` for the dominant kernel (observe) from CUDA events inside the timed region; `cpu_baseline` = the C port
+of the reference's algorithm (oracle/) on this box's host cores.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "65536 batched 40x40 worlds, 32 agents, density 0-0.3, step+observe (BASELINE.json configs[2])"
+H = WD = 40
+N_AGENTS = 32
+FOV, CH = 9, 6
+
+
+def algorithmic_bytes(n_agents=N_AGENTS, h=H, wd=WD, c=CH, f=FOV):
+    """SURVEY.md §8d, per agent-step: step ~ 46 + (H*Wd+8)/N, observe ~ 16 + 4*C*F^2 + (H*Wd+8)/N + 8."""
+    shared = (h * wd + 8) / n_agents
+    step = 46 + shared
+    observe = 16 + 4 * c * f * f + shared + 8
+    return step, observe
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scenario(worlds, seed):
+    from primal_ppo_b200 import random_scenario
+    return random_scenario(worlds, H, WD, N_AGENTS, density=(0.0, 0.3), queue_len=16, seed=seed,
+                           unique_maps=min(256, worlds), fov=FOV, num_channel=CH)
+
+
+def cpu_port_throughput(budget_s, worlds, threads, seed=7):
+    """agent-steps/s of the oracle (C port of the reference's algorithm) on the host cores: the reference's 5-call step
+    + getAllObservations on the same kind of worlds and actions, for ~budget_s seconds."""
+    from oracle import OracleMapfGym, build_oracle
+    from primal_ppo_b200 import random_actions
+    build_oracle()
+    sc = build_scenario(worlds, seed)
+    env = OracleMapfGym(sc, seed=1234, threads=threads, use_tape=False)
+    acts = random_actions(16, worlds, N_AGENTS, seed=seed)
+    out = env.getAllObservations()
+    env.step(acts[0]); env.getAllObservations(out=out)          # warm-up
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        env.step(acts[steps % 16])
+        env.getAllObservations(out=out)
+        steps += 1
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return worlds * N_AGENTS * steps / dt, steps, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path alone (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import max_threads
+    threads = min(max_threads(), len(os.sched_getaffinity(0)))
+    worlds = 32 * threads
+    from oracle import OracleMapfGym, build_oracle
+    from primal_ppo_b200 import random_actions
+    build_oracle()
+    sc = build_scenario(worlds, 7)
+    env = OracleMapfGym(sc, seed=1234, threads=threads, use_tape=False)
+    acts = random_actions(16, worlds, N_AGENTS, seed=7)
+    out = env.getAllObservations()
+    # each bench "step" is a bounded sample: `inner` env steps over `worlds` worlds
+    inner = 8
+    for w in range(args.warmup):
+        for k in range(inner):
+            env.step(acts[k % 16]); env.getAllObservations(out=out)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for k in range(inner):
+            env.step(acts[k % 16]); env.getAllObservations(out=out)
+    dt = time.perf_counter() - t0
+    value = worlds * N_AGENTS * inner * args.steps / dt
+    sample = f"{worlds} worlds 40x40x32 agents x {inner} env steps per bench step, {threads} OpenMP threads"
+    line = {"impl": "reference", "metric": "agent-steps/sec step+observe (40x40, 32 agents)", "value": value,
+            "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/i16 state, f32 obs", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU path on a bounded sample of the same workload"},
+            "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                             "note": "C restatement of mapf_gym.py (oracle/mapf_oracle.c); the Python reference itself "
+                                     "measured 1.4e3 agent-steps/s per core at this shape (SURVEY.md §6) and cannot travel "
+                                     "to the GPU box"},
+            "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--worlds", type=int, default=65536, help="worlds per GPU")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from primal_ppo_b200 import BatchedMapfGym, gae
+    from primal_ppo_b200.build import build
+    build()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Wn, N = args.worlds, N_AGENTS
+    K, Wu = args.steps, max(args.warmup, 3)
+
+    sc = build_scenario(Wn, seed=100 + rank)
+    env = BatchedMapfGym(sc, device=dev, seed=1234 + rank, use_tape=False)
+    obs = torch.empty((Wn, N, CH, FOV, FOV), dtype=torch.float32, device=dev)     # the policy's input tensors
+    vec = torch.empty((Wn, N, 4), dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    ring = [torch.randint(0, 5, (Wn, N), generator=gen, device=dev, dtype=torch.int8) for _ in range(8)]
+    env.getAllObservations(out=(obs, vec))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput (value) + per-kernel CUDA-event timings -----------------------
+    for i in range(Wu):
+        env.step(ring[i % 8]); env.getAllObservations(out=(obs, vec))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for i in range(K):
+            ev[i][0].record()
+            env.step(ring[i % 8])
+            ev[i][1].record()
+            env.getAllObservations(out=(obs, vec))
+            ev[i][2].record()
+        t_end.record()
+        barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    step_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    obs_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = Wn * N * K * world_size / (total_ms_max * 1e-3)
+    err_frac = float((env.state()["err"] != 0).float().mean())
+
+    # ---------------- end to end through the host-buffer C-ABI call ---------------------------------------------
+    hb = env.make_host_buffers(with_obs=False)
+    host_ring = [r.cpu().pin_memory() for r in ring]
+    Ke = max(3, min(K, 20))
+    for i in range(3):
+        hb["actions"].copy_(host_ring[i % 8]); env.step_observe_host(hb, obs, vec)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        hb["actions"].copy_(host_ring[i % 8])                        # the runner's host-side action array
+        h2d, d2h = env.step_observe_host(hb, obs, vec)
+        _ = float(hb["reward"][0, 0])                                # the step's result is read on the host
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = Wn * N * Ke * world_size / float(te.item())
+
+    line_extra = {}
+    if rank == 0 and not args.no_extras:
+        # observations copied to host as well (what the reference's getAllObservations returns): PCIe-bound
+        try:
+            hbo = env.make_host_buffers(with_obs=True)
+            hbo["actions"].copy_(host_ring[0]); env.step_observe_host(hbo, obs, vec)
+            t0 = time.perf_counter()
+            for i in range(2):
+                hbo["actions"].copy_(host_ring[i % 8]); _, d2h_full = env.step_observe_host(hbo, obs, vec)
+            dt = time.perf_counter() - t0
+            line_extra["e2e_obs_to_host"] = {"value": Wn * N * 2 / dt, "unit": "agent-steps/s (1 GPU)",
+                                             "d2h_bytes_per_step": d2h_full, "note": "obs+vec also copied to pinned host memory"}
+            del hbo
+        except Exception as ex:   # host memory for 4 GB pinned buffers may be unavailable
+            line_extra["e2e_obs_to_host"] = {"error": str(ex)[:200]}
+        # BFS maps (all W*N maps of a reset) and GAE (T=256) with their own algorithmic-byte rooflines
+        peak, _ = measured_peaks()
+        nb = min(Wn, 8192)
+        ids = torch.arange(nb * N, device=dev, dtype=torch.int32)
+        bfs_out = torch.empty((nb * N, H, WD), dtype=torch.int16, device=dev)
+        env.bfs_maps(agent_ids=ids, out=bfs_out); torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            env.bfs_maps(agent_ids=ids, out=bfs_out)
+        b.record(); torch.cuda.synchronize(dev)
+        bfs_ms = a.elapsed_time(b) / 3
+        bfs_bytes = nb * N * (2 * H * WD + H * WD / N)
+        line_extra["bfs"] = {"maps": nb * N, "ms": bfs_ms, "maps_per_s": nb * N / (bfs_ms * 1e-3),
+                             "achieved_gbs": bfs_bytes / (bfs_ms * 1e-3) / 1e9, "frac": bfs_bytes / (bfs_ms * 1e-3) / 1e9 / peak}
+        del bfs_out
+        T, cols = 256, 8192 * N
+        r = torch.randn((T, cols), device=dev); v = torch.randn((T, cols), device=dev); lv = torch.randn((cols,), device=dev)
+        gae(r, v, lv); torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(3):
+            gae(r, v, lv)
+        b.record(); torch.cuda.synchronize(dev)
+        gae_ms = a.elapsed_time(b) / 3
+        gae_bytes = 12.0 * T * cols
+        line_extra["gae"] = {"T": T, "cols": cols, "ms": gae_ms, "elements_per_s": T * cols / (gae_ms * 1e-3),
+                             "achieved_gbs": gae_bytes / (gae_ms * 1e-3) / 1e9, "frac": gae_bytes / (gae_ms * 1e-3) / 1e9 / peak}
+        del r, v, lv
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        b_step, b_obs = algorithmic_bytes()
+        obs_bytes = b_obs * Wn * N
+        step_bytes = b_step * Wn * N
+        achieved = obs_bytes / (obs_ms * 1e-3) / 1e9
+        cpu = None
+        if world_size == 1 and args.cpu_budget > 0:
+            from oracle.oracle import max_threads
+            threads = min(max_threads(), len(os.sched_getaffinity(0)))
+            cw = 32 * threads
+            cv, csteps, cdt = cpu_port_throughput(args.cpu_budget, cw, threads)
+            cpu = {"value": cv, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                   "sample": f"{cw} worlds 40x40x32 agents, {csteps} steps in {cdt:.1f} s, {threads} OpenMP threads (oracle/mapf_oracle.c)"}
+        line = {"metric": "agent-steps/sec step+observe (40x40, 32 agents)", "value": value, "unit": "agent-steps/s",
+                "n_gpus": world_size, "steps": K, "warmup": Wu, "ms_per_step": total_ms_max / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16 state, f32 obs", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "worlds_per_gpu": Wn, "agents": N, "grid": [H, WD], "fov": FOV,
+                           "channels": CH, "actions": "uniform random, device-resident ring of 8",
+                           "l2": "working set per step (obs 4.08 GB/GPU written) far exceeds the 126 MB L2; no flush needed",
+                           "worlds_with_error_flags": err_frac},
+                "clocks": clk.summary(),
+                "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": Ke, "note": "mapf_step_observe_host: actions from pinned host memory, per-agent step results "
+                                             "(status, reward, cost, trainValid, goals, violations) copied back every step; "
+                                             "observations stay in HBM as the policy's input tensors"},
+                "gpu_launches": 2 * K,
+                "roofline": {"bound": "hbm", "kernel": "observe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": obs_bytes, "ms_per_launch": obs_ms},
+                "kernels": {"step_kernel": {"ms": step_ms, "algorithmic_bytes": step_bytes,
+                                            "achieved_gbs": step_bytes / (step_ms * 1e-3) / 1e9,
+                                            "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
+                            "observe_kernel": {"ms": obs_ms, "algorithmic_bytes": obs_bytes, "achieved_gbs": achieved,
+                                               "frac": achieved / peak}},
+                "cpu_baseline": cpu}
+        line.update(line_extra)
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

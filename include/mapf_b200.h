@@ -1,0 +1,160 @@
+/*
+ * mapf_b200.h — C ABI of the B200-native batched MAPF environment hot path.
+ *
+ * The reference (Nielsencu/primal-ppo) has no FFI: its environment is a Python class,
+ * `MapfGym` / `FixedMapfGym` (mapf_gym.py:163-669), driven by the rollout loop in runner.py:30-100
+ * and followed by the GAE scan in runner.py:117-149.  This header is the boundary a maintainer binds
+ * instead of those Python methods (INTEGRATION.md shows the ctypes stub): plain pointers and sizes, no
+ * torch types.  Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *  - W worlds, N agents, H x Wd cells, C channels, F = FOV side.  Cells are (row, col).
+ *  - Actions 0..4 = stay, (0,+1), (+1,0), (0,-1), (-1,0)                      (mapf_gym.py:97-98)
+ *  - Unless a function name ends in `_host`, every data pointer is a DEVICE pointer on the env's device
+ *    and the call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *    No allocation and no host synchronisation happens inside reset/evaluate/step/observe/bfs/gae.
+ *  - The caller owns every input/output buffer.  Scenario arrays passed to mapf_reset are BORROWED and
+ *    must stay alive and unchanged until the next mapf_reset / mapf_destroy.
+ *  - Return value: 0 on success, a negative MAPF_E_* code otherwise; mapf_last_error() gives the text.
+ *    Data-dependent failures never abort a call: they set bits in err[w] (MAPF_ERR_*) for that world only.
+ */
+#ifndef MAPF_B200_H
+#define MAPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAPF_B200_ABI_VERSION 1
+
+/* return codes */
+#define MAPF_OK 0
+#define MAPF_E_BAD_CONFIG (-1)
+#define MAPF_E_NULL (-2)
+#define MAPF_E_CUDA (-3)
+#define MAPF_E_UNSUPPORTED (-4)
+#define MAPF_E_STATE (-5)
+
+/* per-world error bits (err[w]); the reference raises or hangs in these situations */
+#define MAPF_ERR_NO_VIABLE 1u    /* IndexError from random.choice([])        mapf_gym.py:588 */
+#define MAPF_ERR_FIX_ITER_CAP 2u /* livelock of the fixActions while loop     mapf_gym.py:563 */
+#define MAPF_ERR_BAD_ACTION 4u   /* action outside 0..4                       mapf_gym.py:452-456 */
+#define MAPF_ERR_TAPE 8u         /* fixActions tape exhausted / inconsistent */
+
+typedef struct MapfEnv MapfEnv; /* opaque; one handle per (process, device); not thread-safe */
+
+/* Replaces the constants read from alg_parameters.py (EnvParameters / NetParameters) and the ctor arguments of
+ * FixedMapfGym (mapf_gym.py:649). */
+typedef struct MapfConfig {
+    int32_t num_worlds;   /* W */
+    int32_t height;       /* H  (max rows over worlds) */
+    int32_t width;        /* Wd (max cols over worlds) */
+    int32_t num_agents;   /* N  = EnvParameters.N_AGENTS  (alg_parameters.py:30); 1..32 for step, any for observe/bfs */
+    int32_t fov;          /* F  = EnvParameters.FOV_SIZE  (alg_parameters.py:33); odd, 3..31 */
+    int32_t num_channel;  /* C  = NetParameters.NUM_CHANNEL (alg_parameters.py:104); 5 or 6 */
+    int32_t use_da;       /* FixedMapfGym(useDA=)  danger-area disc in channel 4   (mapf_gym.py:289-290) */
+    int32_t use_hp;       /* FixedMapfGym(useHP=)  human-path cells in channel 5   (mapf_gym.py:293-297) */
+    int32_t queue_len;    /* Q: goals per agent in goal_queue */
+    int32_t trace_len;    /* L: ticks per world in htrace */
+    int32_t tape_stride;  /* TL: bytes per world in tape; 0 = no tape (Philox mode) */
+    int32_t hp5_per_tick; /* 0: hp5 is [W,5,2]; 1: hp5 is [W,L,5,2] */
+    uint64_t seed;        /* Philox key for the random branch of fixActions when no tape is given */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t reserved;
+} MapfConfig;
+
+/* Exogenous inputs of a batch of worlds — what the reference draws from np.random / random at construction and on
+ * goal arrival (mapf_gym.py:164-190, util.py:67-76) or receives through FixedMapfGym (mapf_gym.py:648-669). */
+typedef struct MapfScenario {
+    const uint8_t *obst;      /* [W,H,Wd]   1 = obstacle (reference -1), 0 = free */
+    const int16_t *starts;    /* [W,N,2]    Sequence.items[0] */
+    const int16_t *goal_queue;/* [W,N,Q,2]  Sequence.items[1:]; the last entry repeats when exhausted (util.py:33-36) */
+    const int16_t *htrace;    /* [W,L,4]    human (pos_r,pos_c,next_r,next_c) per tick (mapf_gym.py:25-50) */
+    const int32_t *hlen;      /* [W]        ticks before the trace wraps to 0 */
+    const int16_t *hp5;       /* [W,5,2] or [W,L,5,2] human.path[1:6], -1 padded; may be NULL unless use_hp */
+    const int8_t *tape;       /* [W,TL]     fixActions tape: [choice, n_evicted, ids...]*; NULL iff tape_stride==0 */
+    const int32_t *tape_len;  /* [W] */
+    const int16_t *dims;      /* [W,2] per-world (rows, cols) or NULL = (H, Wd) for all */
+} MapfScenario;
+
+/* Outputs of one step; any pointer may be NULL (that output is skipped). */
+typedef struct MapfStepOut {
+    int8_t *status;        /* [W,N]   getActionStatus        mapf_gym.py:434-480  (-1,-2,-3,-4,1) */
+    float *reward;         /* [W,N]   calculateActionReward  mapf_gym.py:483-511  (+GOAL_REWARD in mapf_step, runner.py:89-91) */
+    float *cost;           /* [W,N]   calculateCostReward    mapf_gym.py:528-533 */
+    float *train_valid;    /* [W,N,5] getTrainValid          mapf_gym.py:535-550 */
+    uint8_t *goals_reached;/* [W,N]   jointStep()[0]         mapf_gym.py:614-637 */
+    uint8_t *violated;     /* [W,N]   jointStep()[1] */
+    int32_t *shadow_goals; /* [W]     calculateActionReward()[1] */
+    int8_t *fixed_actions; /* [W,N]   the actions actually executed (after fixActions, mapf_gym.py:552-612) */
+} MapfStepOut;
+
+int mapf_abi_version(void);
+const char *mapf_last_error(void);
+
+/* MapfGym.__init__ / FixedMapfGym.__init__ (mapf_gym.py:164-173, 648-663): allocate persistent state. */
+int mapf_create(const MapfConfig *cfg, MapfEnv **out);
+int mapf_destroy(MapfEnv *env);
+
+/* populateMap (mapf_gym.py:175-184): starts, first goals, cleared repetition lists, human tick 0. */
+int mapf_reset(MapfEnv *env, const MapfScenario *scenario, void *stream);
+
+/* getActionStatus + calculateActionReward + calculateCostReward + getTrainValid (runner.py:64-82) without
+ * mutating the env.  out->goals_reached / violated / fixed_actions are ignored. */
+int mapf_evaluate(MapfEnv *env, const int8_t *actions, const MapfStepOut *out, void *stream);
+
+/* jointStep(actions, actionStatus) (mapf_gym.py:614-637, runner.py:87): fixActions, moves, goal arrival, human tick,
+ * constraint violations.  `status` is the array mapf_evaluate produced for the same actions. */
+int mapf_joint_step(MapfEnv *env, const int8_t *actions, const int8_t *status, uint8_t *goals_reached,
+                    uint8_t *violated, int8_t *fixed_actions, void *stream);
+
+/* The five calls of runner.py:64-87 fused in one launch, plus `rewards[goalsReached==1] += GOAL_REWARD`
+ * (runner.py:89-91). */
+int mapf_step(MapfEnv *env, const int8_t *actions, const MapfStepOut *out, void *stream);
+
+/* getAllObservations (mapf_gym.py:327-336): obs f32 [W,N,C,F,F], vec f32 [W,N,4], written in place. */
+int mapf_observe(MapfEnv *env, float *obs, float *vec, void *stream);
+
+/* makeBfsMap (mapf_gym.py:211-244) for the CURRENT goals.  agent_list: n flat ids (w*N+i), or NULL for all W*N
+ * agents in order.  out: int16 [n,H,Wd]: -1 obstacle (and cells outside a world's dims), -2 unreached, >=0 distance. */
+int mapf_bfs(MapfEnv *env, const int32_t *agent_list, int64_t n, int16_t *out, void *stream);
+
+/* The in-loop refresh `makeBfsMap(agent)` on goal arrival (mapf_gym.py:627): recompute, in place, the maps of the
+ * agents with goals_reached[w,i] == 1 inside bfs_maps int16 [W,N,H,Wd].  The arrival list is compacted on the device;
+ * there is no host synchronisation. */
+int mapf_bfs_refresh(MapfEnv *env, const uint8_t *goals_reached, int16_t *bfs_maps, void *stream);
+
+/* GAE + returns of one stream (runner.py:120-149): r, v [T,cols]; last_v [cols]; nonterminal [T,cols] or NULL = all 1
+ * (the reference uses the constant 1.0, runner.py:123); returns = adv + v; adv may be NULL.  gamma, lam are the Python
+ * doubles; the kernel multiplies by float(gamma) and float(gamma*lam) without FMA contraction. */
+int mapf_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, double gamma,
+             double lam, int32_t T, int64_t cols, float *returns, float *adv, void *stream);
+
+/* State read-back for checks and checkpoints (device pointers; any may be NULL):
+ * pos/goal int16 [W,N,2], rep int8 [W,N] (the repetition action or -1, mapf_gym.py:161), err u32 [W]. */
+int mapf_get_state(MapfEnv *env, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream);
+
+/* Episode counters accumulated on device (util.py:56-65 OneEpPerformance, filled in runner.py:66-99):
+ * int64 [W,6] = totalGoals, shadowGoals, staticCollide, humanCollide, agentCollide, constraintViolations. */
+int mapf_get_counters(MapfEnv *env, int64_t *counters, void *stream);
+
+/* ---- host-buffer entry points (what a CPU-side runner calls; copies are inside the call) ---------------- */
+
+/* Host mirror of MapfStepOut: PINNED or pageable host memory; any pointer may be NULL. */
+typedef struct MapfStepOutHost {
+    int8_t *status; float *reward; float *cost; float *train_valid; uint8_t *goals_reached; uint8_t *violated;
+    int32_t *shadow_goals; int8_t *fixed_actions;
+} MapfStepOutHost;
+
+/* actions_host -> device, mapf_step, mapf_observe into obs_dev/vec_dev (device; the policy's input tensors),
+ * step outputs -> host, stream synchronised before return.  If obs_host / vec_host are non-NULL the observations are
+ * also copied to the host (what the reference's getAllObservations returns). */
+int mapf_step_observe_host(MapfEnv *env, const int8_t *actions_host, const MapfStepOutHost *out, float *obs_dev,
+                           float *vec_dev, float *obs_host, float *vec_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPF_B200_H */

@@ -1,0 +1,84 @@
+"""ctypes binding of ``libmapf_b200.so`` (the C ABI in ``include/mapf_b200.h``).
+
+There is NO fallback: if the shared library is missing or a CUDA call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmapf_b200.so")
+
+EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_reset", "mapf_evaluate",
+            "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae",
+            "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host"]
+
+ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE = 1, 2, 4, 8
+
+
+class MapfConfig(C.Structure):
+    _fields_ = [("num_worlds", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("num_agents", C.c_int32),
+                ("fov", C.c_int32), ("num_channel", C.c_int32), ("use_da", C.c_int32), ("use_hp", C.c_int32),
+                ("queue_len", C.c_int32), ("trace_len", C.c_int32), ("tape_stride", C.c_int32),
+                ("hp5_per_tick", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class MapfScenario(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("obst", "starts", "goal_queue", "htrace", "hlen", "hp5", "tape", "tape_len", "dims")]
+
+
+class MapfStepOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals",
+                 "fixed_actions")]
+
+
+MapfStepOutHost = MapfStepOut   # same layout, host pointers
+
+
+class MapfError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA library; raises if it has not been built (python -m primal_ppo_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MapfError(f"{LIB_PATH} is missing: build it with `python -m primal_ppo_b200.build` "
+                        f"(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.mapf_abi_version.restype = C.c_int
+    lib.mapf_last_error.restype = C.c_char_p
+    lib.mapf_create.argtypes = [C.POINTER(MapfConfig), C.POINTER(vp)]
+    lib.mapf_destroy.argtypes = [vp]
+    lib.mapf_reset.argtypes = [vp, C.POINTER(MapfScenario), vp]
+    lib.mapf_evaluate.argtypes = [vp, vp, C.POINTER(MapfStepOut), vp]
+    lib.mapf_joint_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.mapf_step.argtypes = [vp, vp, C.POINTER(MapfStepOut), vp]
+    lib.mapf_observe.argtypes = [vp, vp, vp, vp]
+    lib.mapf_bfs.argtypes = [vp, vp, i64, vp, vp]
+    lib.mapf_bfs_refresh.argtypes = [vp, vp, vp, vp]
+    lib.mapf_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp, vp, vp]
+    lib.mapf_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.mapf_get_counters.argtypes = [vp, vp, vp]
+    lib.mapf_step_observe_host.argtypes = [vp, vp, C.POINTER(MapfStepOutHost), vp, vp, vp, vp, vp]
+    for n in EXPORTED:
+        if n not in ("mapf_last_error",):
+            getattr(lib, n).restype = C.c_int
+    lib.mapf_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load_library().mapf_last_error().decode("utf-8", "replace")
+        raise MapfError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,95 @@
+// common.cuh — shared device-side definitions of the B200 MAPF hot path (sm_100a).
+//
+// HBM layout (all env-owned buffers are SoA over worlds, allocated once in mapf_create):
+//   obst_bits u32 [W, HP, RW]  obstacle / out-of-bounds bit rows, padded by P cells on every side (1 = blocked);
+//                              HP = H + 2P rows, row bit (c + P) is cell c.  384 B per 40x40 world instead of 1600 B.
+//   pos, goal i16 [W,N,2]      agent cell and current goal (row, col)
+//   rep       i8  [W,N]        Agent.invalidActions[2]: the one repetition action, -1 when empty (mapf_gym.py:158-161)
+//   qcur      i32 [W,N]        goals already handed out from goal_queue (Sequence.curIdx - 1, util.py:33-39)
+//   htick     i32 [W]          human tick into htrace
+//   tape_cur  i32 [W], nstep i32 [W], err u32 [W], counters i64 [W,6]
+// Everything else of the reference's Agent objects (invalid lists, restricted dict, good list) is a pure function of
+// this state and is recomputed in registers at the start of every step.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mapf_b200.h"
+
+namespace mapf {
+
+constexpr int NA = 5;                 // EnvParameters.N_ACTIONS (alg_parameters.py:31)
+constexpr int WARPS_PER_BLOCK = 8;    // one warp per world, 8 worlds per 256-thread CTA
+constexpr unsigned FULL = 0xffffffffu;
+
+// status codes of getActionStatus (mapf_gym.py:440-444)
+constexpr int ST_STATIC = -1, ST_HUMAN = -2, ST_AGENT = -3, ST_REPEAT = -4, ST_OK = 1;
+
+struct EnvView {
+    int W, H, Wd, N, F, C, use_da, use_hp, Q, L, TL, hp5_per_tick;
+    int P;        // padding of obst_bits / the agent-id grid = max(2, F/2)
+    int HP;       // H + 2P
+    int RW;       // u32 words per padded bit row (+1 spare word so a funnel read of word k+1 is always in range)
+    int GS;       // byte stride of one row of the shared-memory agent-id grid (multiple of 16)
+    unsigned long long seed;
+    // borrowed scenario
+    const uint8_t *obst;
+    const int16_t *starts, *goal_queue, *htrace, *hp5, *dims;
+    const int32_t *hlen, *tape_len;
+    const int8_t *tape;
+    // owned state
+    uint32_t *obst_bits;
+    int16_t *pos, *goal;
+    int8_t *rep;
+    int32_t *qcur, *htick, *tape_cur, *nstep;
+    uint32_t *err;
+    long long *counters;
+};
+
+__device__ __forceinline__ int dr_of(int a) { return (a == 2) - (a == 4); }   // mapf_gym.py:97
+__device__ __forceinline__ int dc_of(int a) { return (a == 1) - (a == 3); }
+__device__ __forceinline__ int opp_of(int a) { return a == 0 ? 0 : ((a + 1) & 3) + 1; }  // {0:0,1:3,2:4,3:1,4:2} (:100)
+
+// F <= 31 bits of a padded bit row starting at bit `off` (row has RW words, the last one spare).
+__device__ __forceinline__ uint32_t row_window(const uint32_t *row, int off, int nbits) {
+    const int k = off >> 5;
+    const uint32_t v = __funnelshift_r(row[k], row[k + 1], off & 31);
+    return v & ((1u << nbits) - 1u);
+}
+__device__ __forceinline__ uint32_t row_bit(const uint32_t *row, int off) { return (row[off >> 5] >> (off & 31)) & 1u; }
+
+// Philox4x32-10, counter = (world, step, draw, tag), key = seed: the stand-in for Python's `random.choice`
+// (mapf_gym.py:588) when the caller supplies no tape.  Bit-identical to the oracle's philox_draw.
+__device__ __forceinline__ uint32_t philox_draw(unsigned long long seed, uint32_t world, uint32_t step, uint32_t draw) {
+    uint32_t c0 = world, c1 = step, c2 = draw, c3 = 0x4D415046u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+// streaming 16-byte store: observations are written once and consumed by another kernel much later
+__device__ __forceinline__ void st_stream_v4(float *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// launchers implemented in the .cu files
+cudaError_t launch_reset(const EnvView &v, cudaStream_t s);
+cudaError_t launch_step(const EnvView &v, const int8_t *actions, const int8_t *status_in, const MapfStepOut &out,
+                        int mode, cudaStream_t s);
+cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, cudaStream_t s);
+cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
+                       int scatter, cudaStream_t s);
+cudaError_t launch_arrivals(const EnvView &v, const uint8_t *goals, int32_t *list, int32_t *n_dev, cudaStream_t s);
+cudaError_t launch_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, float g, float gl,
+                       int T, long long cols, float *ret, float *adv, cudaStream_t s);
+
+constexpr int MODE_EVALUATE = 0, MODE_JOINT = 1, MODE_FUSED = 2;
+
+}  // namespace mapf

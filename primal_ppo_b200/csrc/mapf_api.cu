@@ -1,0 +1,298 @@
+// mapf_api.cu — the C ABI declared in include/mapf_b200.h (handle, reset, argument checking, host-buffer calls).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+using namespace mapf;
+
+struct MapfEnv {
+    MapfConfig cfg;
+    EnvView v;
+    bool has_scenario;
+    // staging for the *_host entry points (allocated on first use)
+    int8_t *d_actions;
+    MapfStepOut d_out;
+    bool staging;
+    // arrivals compaction scratch for mapf_bfs_refresh
+    int32_t *d_list, *d_count;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+    return fail(MAPF_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+    } while (0)
+
+namespace mapf {
+namespace {
+
+// populateMap (mapf_gym.py:175-184) + packing of the obstacle map into padded bit rows. One warp per world.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) reset_kernel(const EnvView v) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (w >= v.W) return;
+    const int rows = v.dims ? v.dims[2 * w] : v.H, cols = v.dims ? v.dims[2 * w + 1] : v.Wd;
+    const uint8_t *ob = v.obst + (size_t)w * v.H * v.Wd;
+    uint32_t *dst = v.obst_bits + (size_t)w * v.HP * v.RW;
+    for (int k = lane; k < v.HP * v.RW; k += 32) {
+        const int pr = k / v.RW, q = k - pr * v.RW;
+        const int r = pr - v.P;
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int c = q * 32 + b - v.P;
+            const bool blocked = r < 0 || r >= rows || c < 0 || c >= cols || ob[r * v.Wd + c] != 0;
+            bits |= (blocked ? 1u : 0u) << b;
+        }
+        dst[k] = bits;
+    }
+    for (int i = lane; i < v.N; i += 32) {
+        const size_t idx = (size_t)w * v.N + i;
+        reinterpret_cast<uint32_t *>(v.pos)[idx] = reinterpret_cast<const uint32_t *>(v.starts)[idx];
+        reinterpret_cast<uint32_t *>(v.goal)[idx] = reinterpret_cast<const uint32_t *>(v.goal_queue)[idx * v.Q];
+        v.qcur[idx] = 1;                       // Sequence.getNext consumed the first goal (util.py:33-39)
+        v.rep[idx] = -1;                       // setPos clears the repetition list (mapf_gym.py:134-139)
+    }
+    if (lane == 0) { v.htick[w] = 0; v.tape_cur[w] = 0; v.nstep[w] = 0; v.err[w] = 0; }
+    if (lane < 6) v.counters[(size_t)w * 6 + lane] = 0;
+}
+
+}  // namespace
+
+cudaError_t launch_reset(const EnvView &v, cudaStream_t s) {
+    const int blocks = (v.W + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    reset_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(v);
+    return cudaGetLastError();
+}
+}  // namespace mapf
+
+extern "C" {
+
+int mapf_abi_version(void) { return MAPF_B200_ABI_VERSION; }
+const char *mapf_last_error(void) { return g_err; }
+
+int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
+    if (!cfg || !out) return fail(MAPF_E_NULL, "mapf_create: null argument");
+    *out = nullptr;
+    const MapfConfig &c = *cfg;
+    if (c.num_worlds < 1 || c.height < 1 || c.width < 1 || c.num_agents < 1)
+        return fail(MAPF_E_BAD_CONFIG, "mapf_create: W, H, Wd, N must be >= 1");
+    if (c.height > 128 || c.width > 128) return fail(MAPF_E_UNSUPPORTED, "mapf_create: H, Wd <= 128 supported");
+    if (c.num_agents > 254) return fail(MAPF_E_UNSUPPORTED, "mapf_create: N <= 254 supported");
+    if (c.fov < 3 || c.fov > 31 || (c.fov & 1) == 0) return fail(MAPF_E_BAD_CONFIG, "mapf_create: fov must be odd in 3..31");
+    if (c.num_channel != 5 && c.num_channel != 6) return fail(MAPF_E_BAD_CONFIG, "mapf_create: num_channel must be 5 or 6");
+    if (c.queue_len < 1 || c.trace_len < 1 || c.tape_stride < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_create: bad Q / L / TL");
+    CU(cudaSetDevice(c.device));
+    MapfEnv *e = new (std::nothrow) MapfEnv();
+    if (!e) return fail(MAPF_E_CUDA, "mapf_create: out of host memory");
+    memset(e, 0, sizeof(*e));
+    e->cfg = c;
+    EnvView &v = e->v;
+    v.W = c.num_worlds; v.H = c.height; v.Wd = c.width; v.N = c.num_agents; v.F = c.fov; v.C = c.num_channel;
+    v.use_da = c.use_da; v.use_hp = c.use_hp; v.Q = c.queue_len; v.L = c.trace_len; v.TL = c.tape_stride;
+    v.hp5_per_tick = c.hp5_per_tick; v.seed = c.seed;
+    v.P = c.fov / 2 > 2 ? c.fov / 2 : 2;
+    v.HP = v.H + 2 * v.P;
+    v.RW = (v.Wd + 2 * v.P + 31) / 32 + 1;
+    v.GS = ((v.Wd + 2 * v.P + 15) / 16) * 16;
+    const size_t W = v.W, WN = (size_t)v.W * v.N;
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(p, bytes ? bytes : 1); };
+    alloc((void **)&v.obst_bits, W * v.HP * v.RW * 4);
+    alloc((void **)&v.pos, WN * 4);
+    alloc((void **)&v.goal, WN * 4);
+    alloc((void **)&v.rep, WN);
+    alloc((void **)&v.qcur, WN * 4);
+    alloc((void **)&v.htick, W * 4);
+    alloc((void **)&v.tape_cur, W * 4);
+    alloc((void **)&v.nstep, W * 4);
+    alloc((void **)&v.err, W * 4);
+    alloc((void **)&v.counters, W * 6 * 8);
+    alloc((void **)&e->d_list, WN * 4);
+    alloc((void **)&e->d_count, 4);
+    if (err != cudaSuccess) { mapf_destroy(e); return cuda_fail(err, "mapf_create: cudaMalloc"); }
+    *out = e;
+    return MAPF_OK;
+}
+
+int mapf_destroy(MapfEnv *e) {
+    if (!e) return MAPF_OK;
+    EnvView &v = e->v;
+    cudaFree(v.obst_bits); cudaFree(v.pos); cudaFree(v.goal); cudaFree(v.rep); cudaFree(v.qcur); cudaFree(v.htick);
+    cudaFree(v.tape_cur); cudaFree(v.nstep); cudaFree(v.err); cudaFree(v.counters); cudaFree(e->d_list); cudaFree(e->d_count);
+    if (e->staging) {
+        cudaFree(e->d_actions); cudaFree(e->d_out.status); cudaFree(e->d_out.reward); cudaFree(e->d_out.cost);
+        cudaFree(e->d_out.train_valid); cudaFree(e->d_out.goals_reached); cudaFree(e->d_out.violated);
+        cudaFree(e->d_out.shadow_goals); cudaFree(e->d_out.fixed_actions);
+    }
+    delete e;
+    return MAPF_OK;
+}
+
+int mapf_reset(MapfEnv *e, const MapfScenario *sc, void *stream) {
+    if (!e || !sc) return fail(MAPF_E_NULL, "mapf_reset: null argument");
+    if (!sc->obst || !sc->starts || !sc->goal_queue || !sc->htrace || !sc->hlen)
+        return fail(MAPF_E_NULL, "mapf_reset: obst, starts, goal_queue, htrace, hlen are required");
+    if (e->cfg.tape_stride > 0 && (!sc->tape || !sc->tape_len)) return fail(MAPF_E_NULL, "mapf_reset: tape_stride > 0 needs tape and tape_len");
+    if (e->cfg.use_hp && e->cfg.num_channel == 6 && !sc->hp5) return fail(MAPF_E_NULL, "mapf_reset: use_hp needs hp5");
+    EnvView &v = e->v;
+    v.obst = sc->obst; v.starts = sc->starts; v.goal_queue = sc->goal_queue; v.htrace = sc->htrace; v.hlen = sc->hlen;
+    v.hp5 = sc->hp5; v.tape = sc->tape; v.tape_len = sc->tape_len; v.dims = sc->dims;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(launch_reset(v, (cudaStream_t)stream));
+    e->has_scenario = true;
+    return MAPF_OK;
+}
+
+#define NEED_ENV(name)                                                                     \
+    if (!e) return fail(MAPF_E_NULL, name ": null env");                                   \
+    if (!e->has_scenario) return fail(MAPF_E_STATE, name ": mapf_reset has not been called")
+
+static int check_step_n(const MapfEnv *e, const char *name) {
+    if (e->v.N > 32) return fail(MAPF_E_UNSUPPORTED, "%s: joint-step resolution supports N <= 32 agents per world (got %d)", name, e->v.N);
+    return MAPF_OK;
+}
+
+int mapf_evaluate(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, void *stream) {
+    NEED_ENV("mapf_evaluate");
+    if (!actions || !out) return fail(MAPF_E_NULL, "mapf_evaluate: null argument");
+    if (int rc = check_step_n(e, "mapf_evaluate")) return rc;
+    CU(launch_step(e->v, actions, nullptr, *out, MODE_EVALUATE, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_joint_step(MapfEnv *e, const int8_t *actions, const int8_t *status, uint8_t *goals_reached, uint8_t *violated,
+                    int8_t *fixed_actions, void *stream) {
+    NEED_ENV("mapf_joint_step");
+    if (!actions || !status) return fail(MAPF_E_NULL, "mapf_joint_step: null argument");
+    if (int rc = check_step_n(e, "mapf_joint_step")) return rc;
+    MapfStepOut o;
+    memset(&o, 0, sizeof(o));
+    o.goals_reached = goals_reached; o.violated = violated; o.fixed_actions = fixed_actions;
+    CU(launch_step(e->v, actions, status, o, MODE_JOINT, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_step(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, void *stream) {
+    NEED_ENV("mapf_step");
+    if (!actions || !out) return fail(MAPF_E_NULL, "mapf_step: null argument");
+    if (int rc = check_step_n(e, "mapf_step")) return rc;
+    CU(launch_step(e->v, actions, nullptr, *out, MODE_FUSED, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_observe(MapfEnv *e, float *obs, float *vec, void *stream) {
+    NEED_ENV("mapf_observe");
+    if (!obs || !vec) return fail(MAPF_E_NULL, "mapf_observe: null argument");
+    CU(launch_observe(e->v, obs, vec, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_bfs(MapfEnv *e, const int32_t *agent_list, int64_t n, int16_t *out, void *stream) {
+    NEED_ENV("mapf_bfs");
+    if (!out) return fail(MAPF_E_NULL, "mapf_bfs: null out");
+    if (!agent_list) n = (int64_t)e->v.W * e->v.N;
+    if (n < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_bfs: n < 0");
+    if (n == 0) return MAPF_OK;
+    CU(launch_bfs(e->v, agent_list, n, nullptr, out, 0, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_bfs_refresh(MapfEnv *e, const uint8_t *goals_reached, int16_t *bfs_maps, void *stream) {
+    NEED_ENV("mapf_bfs_refresh");
+    if (!goals_reached || !bfs_maps) return fail(MAPF_E_NULL, "mapf_bfs_refresh: null argument");
+    CU(launch_arrivals(e->v, goals_reached, e->d_list, e->d_count, (cudaStream_t)stream));
+    CU(launch_bfs(e->v, e->d_list, (long long)e->v.W * e->v.N, e->d_count, bfs_maps, 1, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, double gamma, double lam,
+             int32_t T, int64_t cols, float *returns, float *adv, void *stream) {
+    if (!r || !v || !last_v || !returns) return fail(MAPF_E_NULL, "mapf_gae: null argument");
+    if (T < 0 || cols < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_gae: negative size");
+    // runner.py:138-143: GAMMA * next_nonterminal and GAMMA * LAM * next_nonterminal are Python doubles that NumPy
+    // applies to f32 arrays as f32 scalars.
+    const float g = (float)(gamma * 1.0), gl = (float)(gamma * lam * 1.0);
+    CU(launch_gae(r, v, last_v, nonterminal, g, gl, T, cols, returns, adv, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_get_state(MapfEnv *e, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream) {
+    if (!e) return fail(MAPF_E_NULL, "mapf_get_state: null env");
+    const size_t WN = (size_t)e->v.W * e->v.N;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pos) CU(cudaMemcpyAsync(pos, e->v.pos, WN * 4, cudaMemcpyDeviceToDevice, s));
+    if (goal) CU(cudaMemcpyAsync(goal, e->v.goal, WN * 4, cudaMemcpyDeviceToDevice, s));
+    if (rep) CU(cudaMemcpyAsync(rep, e->v.rep, WN, cudaMemcpyDeviceToDevice, s));
+    if (err) CU(cudaMemcpyAsync(err, e->v.err, (size_t)e->v.W * 4, cudaMemcpyDeviceToDevice, s));
+    return MAPF_OK;
+}
+
+int mapf_get_counters(MapfEnv *e, int64_t *counters, void *stream) {
+    if (!e || !counters) return fail(MAPF_E_NULL, "mapf_get_counters: null argument");
+    CU(cudaMemcpyAsync(counters, e->v.counters, (size_t)e->v.W * 6 * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfStepOutHost *out, float *obs_dev,
+                           float *vec_dev, float *obs_host, float *vec_host, void *stream) {
+    NEED_ENV("mapf_step_observe_host");
+    if (!actions_host || !out || !obs_dev || !vec_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host: null argument");
+    if (int rc = check_step_n(e, "mapf_step_observe_host")) return rc;
+    const EnvView &v = e->v;
+    const size_t W = v.W, WN = (size_t)v.W * v.N;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!e->staging) {
+        CU(cudaMalloc((void **)&e->d_actions, WN));
+        CU(cudaMalloc((void **)&e->d_out.status, WN));
+        CU(cudaMalloc((void **)&e->d_out.reward, WN * 4));
+        CU(cudaMalloc((void **)&e->d_out.cost, WN * 4));
+        CU(cudaMalloc((void **)&e->d_out.train_valid, WN * NA * 4));
+        CU(cudaMalloc((void **)&e->d_out.goals_reached, WN));
+        CU(cudaMalloc((void **)&e->d_out.violated, WN));
+        CU(cudaMalloc((void **)&e->d_out.shadow_goals, W * 4));
+        CU(cudaMalloc((void **)&e->d_out.fixed_actions, WN));
+        e->staging = true;
+    }
+    CU(cudaMemcpyAsync(e->d_actions, actions_host, WN, cudaMemcpyHostToDevice, s));
+    MapfStepOut o = e->d_out;                                   // only compute what the caller asked for
+    if (!out->status) o.status = nullptr;
+    if (!out->reward) o.reward = nullptr;
+    if (!out->cost) o.cost = nullptr;
+    if (!out->train_valid) o.train_valid = nullptr;
+    if (!out->goals_reached) o.goals_reached = nullptr;
+    if (!out->violated) o.violated = nullptr;
+    if (!out->shadow_goals) o.shadow_goals = nullptr;
+    if (!out->fixed_actions) o.fixed_actions = nullptr;
+    CU(launch_step(v, e->d_actions, nullptr, o, MODE_FUSED, s));
+    CU(launch_observe(v, obs_dev, vec_dev, s));
+    if (out->status) CU(cudaMemcpyAsync(out->status, o.status, WN, cudaMemcpyDeviceToHost, s));
+    if (out->reward) CU(cudaMemcpyAsync(out->reward, o.reward, WN * 4, cudaMemcpyDeviceToHost, s));
+    if (out->cost) CU(cudaMemcpyAsync(out->cost, o.cost, WN * 4, cudaMemcpyDeviceToHost, s));
+    if (out->train_valid) CU(cudaMemcpyAsync(out->train_valid, o.train_valid, WN * NA * 4, cudaMemcpyDeviceToHost, s));
+    if (out->goals_reached) CU(cudaMemcpyAsync(out->goals_reached, o.goals_reached, WN, cudaMemcpyDeviceToHost, s));
+    if (out->violated) CU(cudaMemcpyAsync(out->violated, o.violated, WN, cudaMemcpyDeviceToHost, s));
+    if (out->shadow_goals) CU(cudaMemcpyAsync(out->shadow_goals, o.shadow_goals, W * 4, cudaMemcpyDeviceToHost, s));
+    if (out->fixed_actions) CU(cudaMemcpyAsync(out->fixed_actions, o.fixed_actions, WN, cudaMemcpyDeviceToHost, s));
+    const size_t PB = (size_t)v.C * v.F * v.F;
+    if (obs_host) CU(cudaMemcpyAsync(obs_host, obs_dev, WN * PB * 4, cudaMemcpyDeviceToHost, s));
+    if (vec_host) CU(cudaMemcpyAsync(vec_host, vec_dev, WN * 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return MAPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+"""BatchedMapfGym — the reference env's method surface over W lockstep worlds on one B200.
+
+Drop-in for ``MapfGym`` / ``FixedMapfGym`` (``mapf_gym.py:163-669``) as the rollout loop uses them
+(``runner.py:30-100``): same method names, same argument order, same values; every array gains a leading world
+dimension W and lives on the GPU as a torch tensor.  All arithmetic is done by the hand-written sm_100a kernels
+behind the C ABI of ``include/mapf_b200.h``; torch is used for device memory and streams only.  There is no CPU
+path: constructing the env without CUDA or without the built library raises.
+
+Reference call                                     | batched call
+---------------------------------------------------|---------------------------------------------------------
+``env = FixedMapfGym(obst, seqs, hStart, hGoal)``  | ``env = BatchedMapfGym(scenario)``  (``scenario.py``)
+``obs, vec = env.getAllObservations()``            | same -> f32 [W,N,C,F,F], f32 [W,N,4]
+``st = env.getActionStatus(a)``                    | same -> int8 [W,N]
+``r, sg = env.calculateActionReward(a, st)``       | same -> f32 [W,N], int32 [W]
+``c = env.calculateCostReward(a)``                 | same -> f32 [W,N]
+``tv = env.getTrainValid(a)``                      | same -> f32 [W,N,5]
+``g, cv = env.jointStep(a, st)``                   | same -> u8 [W,N], u8 [W,N]
+(the five calls + ``rewards[g==1] += GOAL_REWARD``)| ``env.step(a)`` -> ``StepOut`` (one fused launch)
+``agent.bfsMap``                                   | ``env.bfs_maps()`` -> int16 [W,N,H,Wd]
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .scenario import Scenario
+
+
+@dataclass
+class StepOut:
+    status: torch.Tensor         # int8  [W,N]
+    reward: torch.Tensor         # f32   [W,N]  (goal bonus included)
+    cost: torch.Tensor           # f32   [W,N]
+    train_valid: torch.Tensor    # f32   [W,N,5]
+    goals_reached: torch.Tensor  # uint8 [W,N]
+    violated: torch.Tensor       # uint8 [W,N]
+    shadow_goals: torch.Tensor   # int32 [W]
+    fixed_actions: torch.Tensor  # int8  [W,N]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedMapfGym:
+    def __init__(self, scenario: Scenario, device=None, seed: int = 1234, use_tape: bool = True):
+        if not torch.cuda.is_available():
+            raise _cabi.MapfError("BatchedMapfGym needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._lib = _cabi.load_library()
+        scenario.validate()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        sc = scenario
+        self.W, self.H, self.Wd, self.N = sc.num_worlds, sc.height, sc.width, sc.num_agents
+        self.F, self.C = sc.fov, sc.num_channel
+        self.num_channel, self.use_da, self.use_hp = sc.num_channel, sc.use_da, sc.use_hp
+        tape = sc.tape if (use_tape and sc.tape is not None) else None
+
+        def up(a):
+            return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        # scenario arrays are borrowed by the C side: keep them alive here
+        self._sc = dict(obst=up(sc.obst), starts=up(sc.starts), goal_queue=up(sc.goal_queue), htrace=up(sc.htrace),
+                        hlen=up(sc.hlen), hp5=up(sc.hp5), tape=up(tape),
+                        tape_len=up(sc.tape_len) if tape is not None else None, dims=up(sc.dims))
+        cfg = _cabi.MapfConfig(num_worlds=self.W, height=self.H, width=self.Wd, num_agents=self.N, fov=self.F,
+                               num_channel=self.C, use_da=int(sc.use_da), use_hp=int(sc.use_hp),
+                               queue_len=int(sc.goal_queue.shape[2]), trace_len=int(sc.htrace.shape[1]),
+                               tape_stride=0 if tape is None else int(tape.shape[1]),
+                               hp5_per_tick=int(sc.hp5 is not None and sc.hp5.ndim == 4), seed=seed,
+                               device=self.device.index or 0, reserved=0)
+        h = C.c_void_p()
+        _cabi.check(self._lib.mapf_create(C.byref(cfg), C.byref(h)), "mapf_create")
+        self._h = h
+        W, N, dev = self.W, self.N, self.device
+        self._out = StepOut(status=torch.empty((W, N), dtype=torch.int8, device=dev),
+                            reward=torch.empty((W, N), dtype=torch.float32, device=dev),
+                            cost=torch.empty((W, N), dtype=torch.float32, device=dev),
+                            train_valid=torch.empty((W, N, 5), dtype=torch.float32, device=dev),
+                            goals_reached=torch.empty((W, N), dtype=torch.uint8, device=dev),
+                            violated=torch.empty((W, N), dtype=torch.uint8, device=dev),
+                            shadow_goals=torch.empty((W,), dtype=torch.int32, device=dev),
+                            fixed_actions=torch.empty((W, N), dtype=torch.int8, device=dev))
+        self._obs = None
+        self._vec = None
+        self._eval_key = None
+        self._bfs = None
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.mapf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        """``populateMap`` (mapf_gym.py:175-184): back to the scenario's starts / first goals / tick 0."""
+        s = self._sc
+        sc = _cabi.MapfScenario(**{k: (None if v is None else v.data_ptr()) for k, v in s.items()})
+        _cabi.check(self._lib.mapf_reset(self._h, C.byref(sc), self._stream()), "mapf_reset")
+        self._eval_key = None
+
+    def _actions(self, actions) -> torch.Tensor:
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+        if a.dtype != torch.int8:
+            a = a.to(torch.int8)
+        a = a.to(self.device, non_blocking=True).contiguous()
+        if tuple(a.shape) != (self.W, self.N):
+            raise ValueError(f"actions must have shape {(self.W, self.N)}, got {tuple(a.shape)}")  # mapf_gym.py:437
+        return a
+
+    def _step_out(self, o: StepOut, **skip) -> _cabi.MapfStepOut:
+        return _cabi.MapfStepOut(status=o.status.data_ptr(), reward=o.reward.data_ptr(), cost=o.cost.data_ptr(),
+                                 train_valid=o.train_valid.data_ptr(), goals_reached=o.goals_reached.data_ptr(),
+                                 violated=o.violated.data_ptr(), shadow_goals=o.shadow_goals.data_ptr(),
+                                 fixed_actions=o.fixed_actions.data_ptr())
+
+    # ---- the reference's five step calls (runner.py:64-87) -----------------------------------------------------
+    def _evaluate(self, actions):
+        a = self._actions(actions)
+        key = (a.data_ptr(), a._version, id(actions))
+        if self._eval_key != key:
+            so = self._step_out(self._out)
+            _cabi.check(self._lib.mapf_evaluate(self._h, _ptr(a), C.byref(so), self._stream()), "mapf_evaluate")
+            self._eval_key = key
+            self._eval_actions = a
+        return self._out
+
+    def getActionStatus(self, actions):
+        self._eval_key = None
+        return self._evaluate(actions).status
+
+    def calculateActionReward(self, actions, actionStatus=None):
+        o = self._evaluate(actions)
+        return o.reward, o.shadow_goals
+
+    def calculateCostReward(self, actions):
+        return self._evaluate(actions).cost
+
+    def getTrainValid(self, actions):
+        return self._evaluate(actions).train_valid
+
+    def jointStep(self, actions, actionStatus):
+        a = self._actions(actions)
+        st = actionStatus.to(device=self.device, dtype=torch.int8).contiguous()
+        o = self._out
+        _cabi.check(self._lib.mapf_joint_step(self._h, _ptr(a), _ptr(st), _ptr(o.goals_reached), _ptr(o.violated),
+                                              _ptr(o.fixed_actions), self._stream()), "mapf_joint_step")
+        self._eval_key = None
+        return o.goals_reached, o.violated
+
+    # ---- fused step -------------------------------------------------------------------------------------------
+    def step(self, actions, out: Optional[StepOut] = None) -> StepOut:
+        """All five calls in one launch plus ``rewards[goalsReached==1] += GOAL_REWARD`` (runner.py:89-91).
+        ``out`` lets a rollout buffer receive the results in place (e.g. slices ``buf.reward[t]``)."""
+        a = self._actions(actions)
+        o = self._out if out is None else out
+        so = self._step_out(o)
+        _cabi.check(self._lib.mapf_step(self._h, _ptr(a), C.byref(so), self._stream()), "mapf_step")
+        self._eval_key = None
+        return o
+
+    # ---- observations -----------------------------------------------------------------------------------------
+    def getAllObservations(self, out=None):
+        """``getAllObservations`` (mapf_gym.py:327-336).  ``out=(obs, vec)`` writes straight into the policy's input
+        tensors; otherwise env-owned tensors are (re)used."""
+        if out is None:
+            if self._obs is None:
+                self._obs = torch.empty((self.W, self.N, self.C, self.F, self.F), dtype=torch.float32, device=self.device)
+                self._vec = torch.empty((self.W, self.N, 4), dtype=torch.float32, device=self.device)
+            obs, vec = self._obs, self._vec
+        else:
+            obs, vec = out
+            assert obs.is_contiguous() and vec.is_contiguous() and obs.dtype == torch.float32 and vec.dtype == torch.float32
+            assert obs.numel() == self.W * self.N * self.C * self.F * self.F and vec.numel() == self.W * self.N * 4
+        _cabi.check(self._lib.mapf_observe(self._h, _ptr(obs), _ptr(vec), self._stream()), "mapf_observe")
+        return obs, vec
+
+    # ---- BFS distance-to-goal maps (agent.bfsMap, mapf_gym.py:211-244) -------------------------------------------
+    def bfs_maps(self, agent_ids: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+        """All maps [W,N,H,Wd] int16 for the current goals, or the maps of the given flat agent ids (w*N+i)."""
+        if agent_ids is None:
+            n = self.W * self.N
+            shape = (self.W, self.N, self.H, self.Wd)
+            lst = None
+        else:
+            lst = agent_ids.to(device=self.device, dtype=torch.int32).contiguous()
+            n = int(lst.numel())
+            shape = (n, self.H, self.Wd)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.int16, device=self.device)
+        _cabi.check(self._lib.mapf_bfs(self._h, _ptr(lst), n, _ptr(out), self._stream()), "mapf_bfs")
+        return out
+
+    def refresh_bfs(self, bfs_maps: torch.Tensor, goals_reached: Optional[torch.Tensor] = None):
+        """In-place refresh of the maps of agents that just received a new goal (mapf_gym.py:627); no host sync."""
+        g = self._out.goals_reached if goals_reached is None else goals_reached
+        _cabi.check(self._lib.mapf_bfs_refresh(self._h, _ptr(g), _ptr(bfs_maps), self._stream()), "mapf_bfs_refresh")
+        return bfs_maps
+
+    # ---- state / counters ---------------------------------------------------------------------------------------
+    def state(self):
+        W, N, dev = self.W, self.N, self.device
+        pos = torch.empty((W, N, 2), dtype=torch.int16, device=dev)
+        goal = torch.empty((W, N, 2), dtype=torch.int16, device=dev)
+        rep = torch.empty((W, N), dtype=torch.int8, device=dev)
+        err = torch.empty((W,), dtype=torch.int32, device=dev)
+        _cabi.check(self._lib.mapf_get_state(self._h, _ptr(pos), _ptr(goal), _ptr(rep), _ptr(err), self._stream()),
+                    "mapf_get_state")
+        return dict(pos=pos, goal=goal, rep=rep, err=err)
+
+    def counters(self):
+        """OneEpPerformance counters per world (util.py:56-65): int64 [W,6] =
+        totalGoals, shadowGoals, staticCollide, humanCollide, agentCollide, constraintViolations."""
+        c = torch.empty((self.W, 6), dtype=torch.int64, device=self.device)
+        _cabi.check(self._lib.mapf_get_counters(self._h, _ptr(c), self._stream()), "mapf_get_counters")
+        return c
+
+    # ---- host-buffer step (what a CPU-side runner calls) ------------------------------------------------------------
+    def make_host_buffers(self, with_obs: bool = False):
+        """Pinned host buffers for ``step_observe_host``."""
+        W, N = self.W, self.N
+        pin = dict(pin_memory=True)
+        hb = dict(actions=torch.zeros((W, N), dtype=torch.int8, **pin),
+                  status=torch.empty((W, N), dtype=torch.int8, **pin),
+                  reward=torch.empty((W, N), dtype=torch.float32, **pin),
+                  cost=torch.empty((W, N), dtype=torch.float32, **pin),
+                  train_valid=torch.empty((W, N, 5), dtype=torch.float32, **pin),
+                  goals_reached=torch.empty((W, N), dtype=torch.uint8, **pin),
+                  violated=torch.empty((W, N), dtype=torch.uint8, **pin),
+                  shadow_goals=torch.empty((W,), dtype=torch.int32, **pin))
+        if with_obs:
+            hb["obs"] = torch.empty((W, N, self.C, self.F, self.F), dtype=torch.float32, **pin)
+            hb["vec"] = torch.empty((W, N, 4), dtype=torch.float32, **pin)
+        return hb
+
+    def step_observe_host(self, hb: dict, obs_dev: torch.Tensor, vec_dev: torch.Tensor):
+        """actions (host) -> H2D -> step -> observe -> results D2H, synchronised.  Returns bytes moved (h2d, d2h)."""
+        so = _cabi.MapfStepOutHost(status=hb["status"].data_ptr(), reward=hb["reward"].data_ptr(),
+                                   cost=hb["cost"].data_ptr(), train_valid=hb["train_valid"].data_ptr(),
+                                   goals_reached=hb["goals_reached"].data_ptr(), violated=hb["violated"].data_ptr(),
+                                   shadow_goals=hb["shadow_goals"].data_ptr(), fixed_actions=None)
+        oh = hb.get("obs")
+        vh = hb.get("vec")
+        _cabi.check(self._lib.mapf_step_observe_host(self._h, _ptr(hb["actions"]), C.byref(so), _ptr(obs_dev),
+                                                     _ptr(vec_dev), _ptr(oh), _ptr(vh), self._stream()),
+                    "mapf_step_observe_host")
+        h2d = hb["actions"].numel()
+        d2h = sum(hb[k].numel() * hb[k].element_size() for k in
+                  ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals"))
+        if oh is not None:
+            d2h += oh.numel() * 4 + vh.numel() * 4
+        return h2d, d2h
+
+
+def gae(rewards: torch.Tensor, values: torch.Tensor, last_values: torch.Tensor, gamma: float = 0.95,
+        lam: float = 0.95, nonterminal: Optional[torch.Tensor] = None, return_advantages: bool = False):
+    """GAE + returns (runner.py:120-149) on device.  rewards, values: f32 [T, ...]; last_values: f32 [...]."""
+    lib = _cabi.load_library()
+    assert rewards.is_cuda and rewards.dtype == torch.float32 and values.dtype == torch.float32
+    r, v, lv = rewards.contiguous(), values.contiguous(), last_values.contiguous().to(torch.float32)
+    T = int(r.shape[0])
+    cols = int(r.numel() // max(T, 1))
+    assert v.shape == r.shape and lv.numel() == cols
+    ret = torch.empty_like(r)
+    adv = torch.empty_like(r) if return_advantages else None
+    nt = None if nonterminal is None else nonterminal.to(torch.uint8).contiguous()
+    stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+    with torch.cuda.device(r.device):
+        _cabi.check(lib.mapf_gae(_ptr(r), _ptr(v), _ptr(lv), _ptr(nt), float(gamma), float(lam), T, cols, _ptr(ret),
+                                 _ptr(adv), stream), "mapf_gae")
+    return (ret, adv) if return_advantages else ret

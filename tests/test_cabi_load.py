@@ -1,0 +1,65 @@
+"""CPU-side checks of the boundary: the CUDA library builds, loads and exports every symbol include/mapf_b200.h
+declares.  No compute calls are made (there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from primal_ppo_b200.build import build
+    return build()
+
+
+def test_header_symbols_exported(lib_path):
+    hdr = open(os.path.join(ROOT, "include", "mapf_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mapf_[a-z_0-9]+)\s*\(", body))
+    assert {"mapf_create", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_gae"} <= declared
+    lib = ctypes.CDLL(lib_path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in mapf_b200.h but not exported"
+    lib.mapf_abi_version.restype = ctypes.c_int
+    m = re.search(r"#define MAPF_B200_ABI_VERSION (\d+)", hdr)
+    assert lib.mapf_abi_version() == int(m.group(1))
+
+
+def test_python_binding_lists_every_symbol(lib_path):
+    from primal_ppo_b200 import _cabi
+    hdr = open(os.path.join(ROOT, "include", "mapf_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mapf_[a-z_0-9]+)\s*\(", body))
+    assert declared == set(_cabi.EXPORTED)
+    lib = _cabi.load_library()
+    assert lib.mapf_abi_version() == 1
+
+
+def test_config_struct_layout_matches_header():
+    from primal_ppo_b200 import _cabi
+    assert ctypes.sizeof(_cabi.MapfConfig) == 12 * 4 + 8 + 2 * 4
+    assert _cabi.MapfConfig.seed.offset == 48
+    assert ctypes.sizeof(_cabi.MapfScenario) == 9 * 8
+    assert ctypes.sizeof(_cabi.MapfStepOut) == 8 * 8
+
+
+def test_null_arguments_are_rejected_without_gpu(lib_path):
+    from primal_ppo_b200 import _cabi
+    lib = _cabi.load_library()
+    assert lib.mapf_create(None, None) == -2
+    assert b"null" in lib.mapf_last_error()
+    assert lib.mapf_step(None, None, None, None) == -2
+    assert lib.mapf_gae(None, None, None, None, 0.95, 0.95, 4, 4, None, None, None) == -2
+
+
+def test_env_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from primal_ppo_b200 import BatchedMapfGym, random_scenario
+    from primal_ppo_b200._cabi import MapfError
+    with pytest.raises(MapfError):
+        BatchedMapfGym(random_scenario(2, 8, 8, 2, seed=0))

@@ -1,0 +1,256 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against
+  (1) the reference-generated golden traces (tests/golden/*.npz) and
+  (2) the C oracle on seeded synthetic scenarios at sizes the oracle finishes in seconds,
+plus size-independent properties at BASELINE.json's full size.
+Bar: bit-exact for every integer / byte output AND for every f32 output (rewards, cost, trainValid, obs, vec, GAE)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import ENV_CASES, GOLDEN_DIR, Golden
+from oracle import OracleMapfGym, gae_oracle
+from primal_ppo_b200 import random_actions, random_scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(sc, **kw):
+    from primal_ppo_b200 import BatchedMapfGym
+    return BatchedMapfGym(sc, **kw)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _eq(a, b, msg):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype == np.float32:
+        a, b = a.view(np.uint32), np.asarray(b, dtype=np.float32).view(np.uint32)
+    np.testing.assert_array_equal(a, b, err_msg=msg)
+
+
+@pytest.mark.parametrize("case", ENV_CASES)
+def test_gpu_matches_reference_trace(case):
+    g = Golden(case)
+    env = _env(g.scenario)
+    s = env.state()
+    _eq(_np(s["pos"]), g["pos"][0], "pos0")
+    _eq(_np(s["goal"]), g["goal"][0], "goal0")
+    obs, vec = env.getAllObservations()
+    _eq(_np(obs), g.obs[0].astype(np.float32), "obs0")
+    _eq(_np(vec), g["vec"][0], "vec0")
+    _eq(_np(env.bfs_maps()), g["bfs0"], "bfs0")
+    for t in range(g.T):
+        out = env.step(torch.from_numpy(g["actions"][t]))
+        for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated"):
+            _eq(_np(getattr(out, key)), g[key][t], f"{case} t={t} {key}")
+        _eq(_np(out.shadow_goals), g["shadow"][t], f"{case} t={t} shadow")
+        _eq(_np(out.fixed_actions), g["fixed"][t], f"{case} t={t} fixed")
+        s = env.state()
+        assert not _np(s["err"]).any(), (case, t)
+        _eq(_np(s["pos"]), g["pos"][t + 1], f"{case} t={t} pos")
+        _eq(_np(s["goal"]), g["goal"][t + 1], f"{case} t={t} goal")
+        obs, vec = env.getAllObservations()
+        _eq(_np(obs), g.obs[t + 1].astype(np.float32), f"{case} t={t} obs")
+        _eq(_np(vec), g["vec"][t + 1], f"{case} t={t} vec")
+    _eq(_np(env.bfs_maps()), g["bfsT"], "bfsT")
+
+
+@pytest.mark.parametrize("case", ["g_10x10_n8", "g_8x8_n8_dense"])
+def test_gpu_five_call_api_matches_reference_trace(case):
+    """The reference's own call order (runner.py:64-91) through the split entry points."""
+    g = Golden(case)
+    env = _env(g.scenario)
+    for t in range(g.T):
+        a = torch.from_numpy(g["actions"][t]).cuda()
+        st = env.getActionStatus(a)
+        rw, sg = env.calculateActionReward(a, st)
+        cost = env.calculateCostReward(a)
+        tv = env.getTrainValid(a)
+        _eq(_np(st), g["status"][t], f"t={t} status")
+        _eq(_np(cost), g["cost"][t], f"t={t} cost")
+        _eq(_np(tv), g["train_valid"][t], f"t={t} tv")
+        _eq(_np(sg), g["shadow"][t], f"t={t} shadow")
+        rw = rw.clone()
+        gr, cv = env.jointStep(a, st)
+        rw[gr == 1] += 1.5
+        _eq(_np(rw), g["reward"][t], f"t={t} reward")
+        _eq(_np(gr), g["goals_reached"][t], f"t={t} goals")
+        _eq(_np(cv), g["violated"][t], f"t={t} violated")
+        _eq(_np(env.state()["pos"]), g["pos"][t + 1], f"t={t} pos")
+
+
+def _run_vs_oracle(sc, T, seed=1234, check_obs_every=1, threads=8):
+    orc = OracleMapfGym(sc, seed=seed, threads=threads, use_tape=False)
+    env = _env(sc, seed=seed, use_tape=False)
+    acts = random_actions(T, sc.num_worlds, sc.num_agents, seed=seed)
+    o_obs, o_vec = orc.getAllObservations()
+    obs, vec = env.getAllObservations()
+    assert torch.equal(obs, torch.from_numpy(o_obs).cuda()) and torch.equal(vec, torch.from_numpy(o_vec).cuda())
+    for t in range(T):
+        ref = orc.step(acts[t])
+        out = env.step(torch.from_numpy(acts[t]))
+        ok_w = orc.state()["err"] == 0          # worlds where the reference would have raised are excluded
+        e_gpu = _np(env.state()["err"]).astype(np.uint32)
+        np.testing.assert_array_equal(e_gpu, orc.state()["err"], err_msg=f"t={t} err flags")
+        for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated"):
+            _eq(_np(getattr(out, key))[ok_w], ref[key][ok_w], f"t={t} {key}")
+        _eq(_np(out.shadow_goals)[ok_w], ref["shadow"][ok_w], f"t={t} shadow")
+        _eq(_np(out.fixed_actions)[ok_w], ref["fixed"][ok_w], f"t={t} fixed")
+        s, so = env.state(), orc.state()
+        _eq(_np(s["pos"])[ok_w], so["pos"][ok_w], f"t={t} pos")
+        _eq(_np(s["goal"])[ok_w], so["goal"][ok_w], f"t={t} goal")
+        _eq(_np(s["rep"])[ok_w], so["rep"][ok_w], f"t={t} rep")
+        if t % check_obs_every == 0 or t == T - 1:
+            o_obs, o_vec = orc.getAllObservations(out=(o_obs, o_vec))
+            obs, vec = env.getAllObservations()
+            okd = torch.from_numpy(ok_w).cuda()
+            assert torch.equal(obs[okd], torch.from_numpy(o_obs).cuda()[okd]), f"t={t} obs"
+            assert torch.equal(vec[okd], torch.from_numpy(o_vec).cuda()[okd]), f"t={t} vec"
+    _eq(_np(env.bfs_maps())[ok_w], orc.bfs_maps()[ok_w], "bfs")
+    return env, orc
+
+
+def test_gpu_matches_oracle_config2_4096x20x20x8():
+    """BASELINE.json configs[1]: 4096 worlds 20x20, 8 agents, replayed actions, bit-exact step+obs."""
+    sc = random_scenario(4096, 20, 20, 8, density=(0.2, 0.2), queue_len=8, seed=11, unique_maps=256)
+    env, orc = _run_vs_oracle(sc, T=64, check_obs_every=4)
+    # counters accumulated on device equal the sums over the trace (util.py:56-65)
+    assert int(env.counters()[:, 0].sum()) > 0
+
+
+def test_gpu_matches_oracle_config3_shape_40x40x32():
+    sc = random_scenario(768, 40, 40, 32, density=(0.0, 0.3), queue_len=8, seed=12, unique_maps=96)
+    _run_vs_oracle(sc, T=32, check_obs_every=4)
+
+
+def test_gpu_matches_oracle_crowded_fixactions_philox():
+    """8x8, 8 agents, density up to 0.3: fixActions branch 3 (Philox stand-in) and error flags agree."""
+    sc = random_scenario(2048, 8, 8, 8, density=(0.2, 0.3), queue_len=6, seed=13, unique_maps=256)
+    _run_vs_oracle(sc, T=48)
+
+
+@pytest.mark.parametrize("shape", [(1, 7, 11, 1), (3, 12, 9, 6), (13, 10, 10, 2), (9, 33, 65, 5), (5, 64, 64, 31)])
+def test_gpu_matches_oracle_ragged_shapes(shape):
+    W, H, Wd, N = shape
+    sc = random_scenario(W, H, Wd, N, density=(0.05, 0.2), queue_len=3, seed=W * 7 + N, num_channel=5 if N == 6 else 6)
+    _run_vs_oracle(sc, T=24)
+
+
+def test_gpu_eval_channels_and_large_fov_observe_only():
+    """use_da / use_hp channels and a FOV sweep; N = 128 agents (observe and BFS only: config 5 shape)."""
+    for fov in (9, 15, 21, 31):
+        sc = random_scenario(6, 80, 80, 128, density=(0.0, 0.3), queue_len=2, seed=fov, fov=fov, use_da=True, use_hp=True)
+        orc = OracleMapfGym(sc, threads=8, use_tape=False)
+        env = _env(sc, use_tape=False)
+        o_obs, o_vec = orc.getAllObservations()
+        obs, vec = env.getAllObservations()
+        assert torch.equal(obs, torch.from_numpy(o_obs).cuda()), fov
+        assert torch.equal(vec, torch.from_numpy(o_vec).cuda()), fov
+        if fov == 9:
+            _eq(_np(env.bfs_maps()), orc.bfs_maps(), "bfs 80x80")
+            from primal_ppo_b200._cabi import MapfError
+            with pytest.raises(MapfError):
+                env.step(torch.zeros((6, 128), dtype=torch.int8))
+
+
+def test_gpu_bfs_refresh_in_place():
+    sc = random_scenario(256, 40, 40, 32, density=(0.0, 0.3), queue_len=8, seed=21, unique_maps=32)
+    orc = OracleMapfGym(sc, threads=8, use_tape=False)
+    env = _env(sc, use_tape=False)
+    maps = env.bfs_maps()
+    rng = np.random.default_rng(0)
+    total = 0
+    for t in range(24):
+        # walk down the BFS field so that goals are reached
+        m = _np(maps)
+        s = orc.state()
+        acts = rng.integers(0, 5, size=(sc.num_worlds, sc.num_agents)).astype(np.int8)
+        pos = s["pos"].astype(np.int64)
+        for k, (dr, dc) in enumerate([(0, 1), (1, 0), (0, -1), (-1, 0)], start=1):
+            rr = np.clip(pos[..., 0] + dr, 0, 39)
+            cc = np.clip(pos[..., 1] + dc, 0, 39)
+            w_i = np.arange(sc.num_worlds)[:, None]
+            a_i = np.arange(sc.num_agents)[None, :]
+            here = m[w_i, a_i, pos[..., 0], pos[..., 1]]
+            nxt = m[w_i, a_i, rr, cc]
+            acts = np.where((nxt >= 0) & (nxt < here), k, acts).astype(np.int8)
+        orc.step(acts)
+        out = env.step(torch.from_numpy(acts))
+        total += int(out.goals_reached.sum())
+        env.refresh_bfs(maps)
+        _eq(_np(maps), orc.bfs_maps(), f"t={t} refreshed maps")
+    assert total > 100
+
+
+def test_gpu_gae_bit_exact():
+    d = np.load(GOLDEN_DIR + "/gae_runner.npz")
+    from primal_ppo_b200 import gae
+    ret = gae(torch.from_numpy(d["rewards"]).cuda(), torch.from_numpy(d["values"]).cuda(),
+              torch.from_numpy(d["last_values"]).cuda(), float(d["gamma"]), float(d["lam"]))
+    _eq(_np(ret), d["returns"], "golden returns")
+    cret = gae(torch.from_numpy(d["cost_rewards"]).cuda(), torch.from_numpy(d["cost_values"]).cuda(),
+               torch.from_numpy(d["last_cost_values"]).cuda(), float(d["gamma"]), float(d["lam"]))
+    _eq(_np(cret), d["cost_returns"], "golden cost returns")
+    rng = np.random.default_rng(5)
+    for T, cols in ((256, 4096 * 8), (256, 1000 * 3), (1, 64), (7, 5)):
+        r = rng.normal(size=(T, cols)).astype(np.float32)
+        v = rng.normal(size=(T, cols)).astype(np.float32)
+        lv = rng.normal(size=(cols,)).astype(np.float32)
+        ref, radv = gae_oracle(r, v, lv)
+        ret, adv = gae(torch.from_numpy(r).cuda(), torch.from_numpy(v).cuda(), torch.from_numpy(lv).cuda(),
+                       return_advantages=True)
+        _eq(_np(ret), ref, f"gae returns {T}x{cols}")
+        _eq(_np(adv), radv, f"gae adv {T}x{cols}")
+
+
+def test_gpu_host_buffer_call_equals_device_call():
+    sc = random_scenario(512, 20, 20, 8, density=(0.1, 0.2), queue_len=4, seed=31, unique_maps=64)
+    a = random_actions(6, 512, 8, seed=3)
+    e1, e2 = _env(sc, use_tape=False), _env(sc, use_tape=False)
+    hb = e2.make_host_buffers(with_obs=True)
+    obs2 = torch.empty((512, 8, 6, 9, 9), device="cuda")
+    vec2 = torch.empty((512, 8, 4), device="cuda")
+    for t in range(6):
+        o1 = e1.step(torch.from_numpy(a[t]))
+        obs1, vec1 = e1.getAllObservations()
+        hb["actions"].copy_(torch.from_numpy(a[t]))
+        e2.step_observe_host(hb, obs2, vec2)
+        for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals"):
+            _eq(_np(getattr(o1, key)), hb[key].numpy(), key)
+        assert torch.equal(obs1, obs2) and torch.equal(vec1, vec2)
+        assert torch.equal(obs1.cpu(), hb["obs"]) and torch.equal(vec1.cpu(), hb["vec"])
+
+
+def test_gpu_full_size_properties_65536x40x40x32():
+    """BASELINE.json configs[2] at full size: properties that do not need the oracle."""
+    W, N, H = 65536, 32, 40
+    sc = random_scenario(W, H, H, N, density=(0.0, 0.3), queue_len=8, seed=41, unique_maps=128)
+    env = _env(sc, use_tape=False)
+    obst = torch.from_numpy(sc.obst).cuda()
+    acts = torch.from_numpy(random_actions(4, W, N, seed=9)).cuda()
+    widx = torch.arange(W, device="cuda")[:, None].expand(W, N)
+    for t in range(4):
+        out = env.step(acts[t])
+        s = env.state()
+        ok = s["err"] == 0
+        pos = s["pos"].long()
+        cell = pos[..., 0] * H + pos[..., 1]
+        # in bounds, never on an obstacle, no two agents of a world on one cell
+        assert bool(((pos >= 0) & (pos < H)).all())
+        assert bool((obst[widx, pos[..., 0], pos[..., 1]] == 0)[ok].all())
+        srt = cell.sort(dim=1).values
+        assert bool((srt[:, 1:] != srt[:, :-1])[ok].all())
+        # fixActions post-condition (mapf_gym.py:600-610): executed actions have status 1 or -4 -> moved agents
+        # either stayed or moved exactly one cell
+        assert set(torch.unique(out.status).tolist()) <= {-4, -3, -2, -1, 1}
+        assert set(torch.unique(out.reward).tolist()) <= {float(np.float32(x)) for x in (-2, -0.35, -0.3, -0.5, np.float32(-0.35) + np.float32(1.5), np.float32(-0.3) + np.float32(1.5))}
+        obs, vec = env.getAllObservations()
+        assert bool(((obs == 0) | (obs == 1)).all())
+        assert bool((obs[:, :, 0, 4, 4] == 1).all())          # own cell marked in channel 0
+        assert bool((obs[:, :, 2].sum(dim=(2, 3)) <= 1).all())  # own goal at most once
+        assert bool((obs[:, :, 5] == 0).all())                # channel 5 is all-zero in training
+        # channel 1 never overlaps channel 0
+        assert bool(((obs[:, :, 0] * obs[:, :, 1]) == 0).all())
+    assert float((env.state()["err"] != 0).float().mean()) < 0.01
