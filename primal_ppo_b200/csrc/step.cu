@@ -255,7 +255,9 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
                     scan_diamond(s.grid, GS, gr, gc, lane + 1, s.commit, -1, r2, c2, m2);
                     const uint32_t ok = viable & ~(restr & c2);                   // :577-584
                     int choice;
-                    if (ok) {
+                    if (good) {
+                        choice = __ffs(good) - 1;                                 // an evicted agent may own a good action (:568)
+                    } else if (ok) {
                         choice = __ffs(ok) - 1;
                     } else if (!viable) {
                         errbits |= MAPF_ERR_NO_VIABLE;                            // reference: IndexError (:588)
