@@ -273,6 +273,16 @@ def main():
             line_extra["e2e_obs_to_host"] = {"error": str(ex)[:200]}
         # BFS maps (all W*N maps of a reset) and GAE (T=256) with their own algorithmic-byte rooflines
         peak, _ = measured_peaks()
+        # context for a write-only kernel: how fast a plain device fill of 4 GiB runs on this GPU
+        buf = torch.empty(1 << 30, dtype=torch.float32, device=dev)
+        buf.zero_(); torch.cuda.synchronize(dev)
+        fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fa.record()
+        for _ in range(5):
+            buf.zero_()
+        fb.record(); torch.cuda.synchronize(dev)
+        line_extra["write_only_fill_gbs"] = 5 * buf.numel() * 4 / (fa.elapsed_time(fb) * 1e-3) / 1e9
+        del buf
         nb = min(Wn, 8192)
         ids = torch.arange(nb * N, device=dev, dtype=torch.int32)
         bfs_out = torch.empty((nb * N, H, WD), dtype=torch.int16, device=dev)
@@ -323,9 +333,10 @@ def main():
                            "worlds_with_error_flags": err_frac},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": Ke, "note": "mapf_step_observe_host: actions from pinned host memory, per-agent step results "
-                                             "(status, reward, cost, trainValid, goals, violations) copied back every step; "
-                                             "observations stay in HBM as the policy's input tensors"},
+                        "steps": Ke, "note": "mapf_step_observe_host: actions from pinned host memory; per-agent step results "
+                                             "(status, reward, cost, goals, violations, shadow goals) copied back to pinned host "
+                                             "memory every step; observations and trainValid stay in HBM as the policy's / learner's "
+                                             "input tensors"},
                 "gpu_launches": 2 * K,
                 "roofline": {"bound": "hbm", "kernel": "observe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -149,10 +149,12 @@ typedef struct MapfStepOutHost {
 } MapfStepOutHost;
 
 /* actions_host -> device, mapf_step, mapf_observe into obs_dev/vec_dev (device; the policy's input tensors),
- * step outputs -> host, stream synchronised before return.  If obs_host / vec_host are non-NULL the observations are
- * also copied to the host (what the reference's getAllObservations returns). */
+ * step outputs -> host, stream synchronised before return.  train_valid_dev (device, optional) receives trainValid
+ * [W,N,5] in HBM — like the observations it is training data that the learner consumes on the GPU; it is copied to the
+ * host only if out->train_valid is non-NULL.  If obs_host / vec_host are non-NULL the observations are also copied to
+ * the host (what the reference's getAllObservations returns). */
 int mapf_step_observe_host(MapfEnv *env, const int8_t *actions_host, const MapfStepOutHost *out, float *obs_dev,
-                           float *vec_dev, float *obs_host, float *vec_host, void *stream);
+                           float *vec_dev, float *train_valid_dev, float *obs_host, float *vec_host, void *stream);
 
 #ifdef __cplusplus
 }

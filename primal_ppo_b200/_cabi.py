@@ -69,7 +69,7 @@ def load_library():
     lib.mapf_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp, vp, vp]
     lib.mapf_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.mapf_get_counters.argtypes = [vp, vp, vp]
-    lib.mapf_step_observe_host.argtypes = [vp, vp, C.POINTER(MapfStepOutHost), vp, vp, vp, vp, vp]
+    lib.mapf_step_observe_host.argtypes = [vp, vp, C.POINTER(MapfStepOutHost), vp, vp, vp, vp, vp, vp]
     for n in EXPORTED:
         if n not in ("mapf_last_error",):
             getattr(lib, n).restype = C.c_int

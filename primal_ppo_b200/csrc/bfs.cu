@@ -4,8 +4,8 @@
 // -1 obstacle, -2 unreached, >= 0 distance (the goal cell is written 0 even when it is not free, as the reference
 // does).  The reference computes one map per agent at reset and on every goal arrival (:183, :627).
 //
-// Layout: the world's rows are bit masks held in registers, R consecutive rows per lane (lane = row block), NW 32-bit
-// words per row.  One BFS level is
+// Layout: the world's rows are bit masks held in registers; G lanes share one map (G = 8 for H <= 40, so a warp runs
+// four maps at once), R consecutive rows per lane, NW 32-bit words per row.  One BFS level is
 //     next = ((f << 1) | (f >> 1) | f_row_above | f_row_below) & free & ~visited
 // with the rows above/below a lane's block fetched by warp shuffles.  Newly reached cells get the level written into
 // an int16 tile in shared memory; when the wavefront dies the tile (H*Wd*2 bytes, 3200 B for 40x40) leaves with ONE
@@ -25,39 +25,47 @@ __device__ __forceinline__ void bulk_store_g2s_commit_wait(void *gdst, const voi
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <int R, int NW>
+// G lanes cooperate on one map (32/G maps per warp), R consecutive rows per lane, NW 32-bit words per row.
+template <int G, int R, int NW>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long long n_maps_in,
            const int32_t *__restrict__ n_dev, int16_t *__restrict__ out, const int tile_bytes, const int use_tma,
-           const int scatter) {
+           const int scatter, int *__restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int MPW = 32 / G;                                   // maps per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, gl = lane % G;                      // map slot within the warp, lane within the map
     const int H = v.H, Wd = v.Wd, P = v.P, RW = v.RW;
-    int16_t *tile = reinterpret_cast<int16_t *>(smem_raw + (size_t)warp * tile_bytes);
+    int16_t *tile = reinterpret_cast<int16_t *>(smem_raw + ((size_t)warp * MPW + grp) * tile_bytes);
     const int cells = H * Wd;
     const long long n_maps = n_dev ? (long long)*n_dev : n_maps_in;   // device-side count: no host sync for refreshes
 
-    const int wpb = blockDim.x >> 5;
-    for (long long m = (long long)blockIdx.x * wpb + warp; m < n_maps; m += (long long)gridDim.x * wpb) {
-        const long long fid = agent_list ? (long long)agent_list[m] : m;
+    for (;;) {
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(work_counter, MPW);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n_maps) break;
+        const long long m = base + grp;
+        const bool valid = m < n_maps;
+        const long long fid = valid ? (agent_list ? (long long)agent_list[m] : m) : 0;
         const int w = (int)(fid / v.N);
         const uint32_t gw = reinterpret_cast<const uint32_t *>(v.goal)[fid];
-        const int goal_r = (int16_t)(gw & 0xffff), goal_c = (int16_t)(gw >> 16);
+        const int goal_r = valid ? (int16_t)(gw & 0xffff) : -1, goal_c = (int16_t)(gw >> 16);
 
         // tile := -1 everywhere (obstacles keep it; reached cells get their level; the rest -2 at the end)
         {
             uint32_t *t32 = reinterpret_cast<uint32_t *>(tile);
-            for (int k = lane; k < (cells + 1) / 2; k += 32) t32[k] = 0xffffffffu;
+            for (int k = gl; k < (cells + 1) / 2; k += G) t32[k] = 0xffffffffu;
         }
         uint32_t freeb[R][NW], vis[R][NW], fr[R][NW];
         const uint32_t *ob = v.obst_bits + (size_t)w * v.HP * RW;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const int r = lane * R + k;
+            const int r = gl * R + k;
 #pragma unroll
             for (int q = 0; q < NW; ++q) {
                 uint32_t x = 0;
-                if (r < H) {
+                if (r < H && valid) {
                     const uint32_t *row = ob + (size_t)(r + P) * RW;
                     const int i0 = q + (P >> 5);
                     const uint32_t lo = i0 < RW ? __ldg(row + i0) : 0xffffffffu, hi = i0 + 1 < RW ? __ldg(row + i0 + 1) : 0xffffffffu;
@@ -76,21 +84,21 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
             // write the level of the current frontier
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const int r = lane * R + k;
+                const int r = gl * R + k;
 #pragma unroll
                 for (int q = 0; q < NW; ++q) {
                     uint32_t b = fr[k][q];
                     while (b) { const int c = __ffs(b) - 1; b &= b - 1; tile[r * Wd + 32 * q + c] = (int16_t)level; }
                 }
             }
-            // rows adjacent to this lane's block
+            // rows adjacent to this lane's block (lanes of the same map only)
             uint32_t up[NW], dn[NW];
 #pragma unroll
             for (int q = 0; q < NW; ++q) {
-                up[q] = __shfl_up_sync(FULL, fr[R - 1][q], 1);
-                dn[q] = __shfl_down_sync(FULL, fr[0][q], 1);
-                if (lane == 0) up[q] = 0;
-                if (lane == 31) dn[q] = 0;
+                up[q] = __shfl_up_sync(FULL, fr[R - 1][q], 1, G);
+                dn[q] = __shfl_down_sync(FULL, fr[0][q], 1, G);
+                if (gl == 0) up[q] = 0;
+                if (gl == G - 1) dn[q] = 0;
             }
             uint32_t nx[R][NW];
             uint32_t any = 0;
@@ -117,7 +125,7 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
         // free cells the wavefront never reached: -2
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const int r = lane * R + k;
+            const int r = gl * R + k;
 #pragma unroll
             for (int q = 0; q < NW; ++q) {
                 uint32_t b = freeb[k][q] & ~vis[k][q];
@@ -128,11 +136,11 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
         if (use_tma) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) bulk_store_g2s_commit_wait(dst, tile, (uint32_t)(cells * 2));
+            if (gl == 0 && valid) bulk_store_g2s_commit_wait(dst, tile, (uint32_t)(cells * 2));
             __syncwarp();
         } else {
             __syncwarp();
-            for (int k = lane; k < cells; k += 32) dst[k] = tile[k];
+            if (valid) for (int k = gl; k < cells; k += G) dst[k] = tile[k];
             __syncwarp();
         }
     }
@@ -156,39 +164,45 @@ __global__ void arrivals_kernel(const uint8_t *__restrict__ goals, const long lo
     }
 }
 
-template <int R, int NW>
+template <int G, int R, int NW>
 cudaError_t launch_bfs_t(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
-                         int scatter, cudaStream_t stream) {
+                         int scatter, int *work_counter, cudaStream_t stream) {
+    constexpr int MPW = 32 / G;
     const int cells = v.H * v.Wd;
     const int tile_bytes = ((cells * 2 + 127) / 128) * 128;
     const int use_tma = ((cells * 2) % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     int wpb = WARPS_PER_BLOCK;
-    while (wpb > 1 && (size_t)tile_bytes * wpb > 200 * 1024) wpb >>= 1;
-    const size_t smem = (size_t)tile_bytes * wpb;
-    cudaError_t e = cudaFuncSetAttribute(bfs_kernel<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    while (wpb > 1 && (size_t)tile_bytes * MPW * wpb > 110 * 1024) wpb >>= 1;
+    const size_t smem = (size_t)tile_bytes * MPW * wpb;
+    cudaError_t e = cudaFuncSetAttribute(bfs_kernel<G, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_kernel<R, NW>, wpb * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_kernel<G, R, NW>, wpb * 32, smem);
     if (per_sm < 1) per_sm = 1;
-    const long long need = (n + wpb - 1) / wpb;
+    const long long need = (n + (long long)wpb * MPW - 1) / ((long long)wpb * MPW);
     const int blocks = (int)(need < (long long)sms * per_sm ? need : (long long)sms * per_sm);
     if (blocks <= 0) return cudaSuccess;
-    bfs_kernel<R, NW><<<blocks, wpb * 32, smem, stream>>>(v, agent_list, n, n_dev, out, tile_bytes, use_tma, scatter);
+    e = cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    bfs_kernel<G, R, NW><<<blocks, wpb * 32, smem, stream>>>(v, agent_list, n, n_dev, out, tile_bytes, use_tma, scatter, work_counter);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
-                       int scatter, cudaStream_t stream) {
-    const int R = (v.H + 31) / 32, NW = (v.Wd + 31) / 32;
-#define CASE(r, q) if (R == r && NW == q) return launch_bfs_t<r, q>(v, agent_list, n, n_dev, out, scatter, stream);
-    CASE(1, 1) CASE(1, 2) CASE(1, 3) CASE(1, 4)
-    CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(2, 4)
-    CASE(3, 1) CASE(3, 2) CASE(3, 3) CASE(3, 4)
-    CASE(4, 1) CASE(4, 2) CASE(4, 3) CASE(4, 4)
+                       int scatter, int *work_counter, cudaStream_t stream) {
+    // lanes per map: the smallest of 8/16/32 that keeps <= 5 rows per lane
+    const int G = v.H <= 40 ? 8 : v.H <= 80 ? 16 : 32;
+    const int R = (v.H + G - 1) / G, NW = (v.Wd + 31) / 32;
+#define CASE(g, r, q) if (G == g && R == r && NW == q) return launch_bfs_t<g, r, q>(v, agent_list, n, n_dev, out, scatter, work_counter, stream);
+#define CASES_NW(g, r) CASE(g, r, 1) CASE(g, r, 2) CASE(g, r, 3) CASE(g, r, 4)
+    CASES_NW(8, 1) CASES_NW(8, 2) CASES_NW(8, 3) CASES_NW(8, 4) CASES_NW(8, 5)
+    CASES_NW(16, 3) CASES_NW(16, 4) CASES_NW(16, 5)
+    CASES_NW(32, 3) CASES_NW(32, 4)
+#undef CASES_NW
 #undef CASE
     return cudaErrorInvalidValue;
 }

@@ -6,7 +6,7 @@
 //   pos, goal i16 [W,N,2]      agent cell and current goal (row, col)
 //   rep       i8  [W,N]        Agent.invalidActions[2]: the one repetition action, -1 when empty (mapf_gym.py:158-161)
 //   qcur      i32 [W,N]        goals already handed out from goal_queue (Sequence.curIdx - 1, util.py:33-39)
-//   htick     i32 [W]          human tick into htrace
+//   htick     i32 [W]          human tick into htrace;  hcur i16 [W,4] = htrace[w, htick[w]] (saves a dependent load)
 //   tape_cur  i32 [W], nstep i32 [W], err u32 [W], counters i64 [W,6]
 // Everything else of the reference's Agent objects (invalid lists, restricted dict, good list) is a pure function of
 // this state and is recomputed in registers at the start of every step.
@@ -42,6 +42,8 @@ struct EnvView {
     int16_t *pos, *goal;
     int8_t *rep;
     int32_t *qcur, *htick, *tape_cur, *nstep;
+    int16_t *hcur;      // [W,4] the human's (pos, next) of the current tick = htrace[w, htick[w]] (kept by reset/step)
+    int16_t *hnx;       // [W,4] the entry of the following tick (wrapped), so that a step has no dependent loads
     uint32_t *err;
     long long *counters;
 };
@@ -82,10 +84,10 @@ __device__ __forceinline__ void st_stream_v4(float *p, uint32_t a, uint32_t b, u
 // launchers implemented in the .cu files
 cudaError_t launch_reset(const EnvView &v, cudaStream_t s);
 cudaError_t launch_step(const EnvView &v, const int8_t *actions, const int8_t *status_in, const MapfStepOut &out,
-                        int mode, cudaStream_t s);
-cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, cudaStream_t s);
+                        int mode, int *work_counter, cudaStream_t s);
+cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t s);
 cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
-                       int scatter, cudaStream_t s);
+                       int scatter, int *work_counter, cudaStream_t s);
 cudaError_t launch_arrivals(const EnvView &v, const uint8_t *goals, int32_t *list, int32_t *n_dev, cudaStream_t s);
 cudaError_t launch_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, float g, float gl,
                        int T, long long cols, float *ret, float *adv, cudaStream_t s);

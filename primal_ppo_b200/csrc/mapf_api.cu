@@ -18,6 +18,8 @@ struct MapfEnv {
     bool staging;
     // arrivals compaction scratch for mapf_bfs_refresh
     int32_t *d_list, *d_count;
+    int *d_work;   // dynamic-scheduling counter of step_kernel / observe_kernel
+    int *d_work_bfs;
 };
 
 static thread_local char g_err[512] = "";
@@ -67,7 +69,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) reset_kernel(const EnvVi
         v.qcur[idx] = 1;                       // Sequence.getNext consumed the first goal (util.py:33-39)
         v.rep[idx] = -1;                       // setPos clears the repetition list (mapf_gym.py:134-139)
     }
-    if (lane == 0) { v.htick[w] = 0; v.tape_cur[w] = 0; v.nstep[w] = 0; v.err[w] = 0; }
+    if (lane == 0) {
+        v.htick[w] = 0; v.tape_cur[w] = 0; v.nstep[w] = 0; v.err[w] = 0;
+        reinterpret_cast<int2 *>(v.hcur)[w] = *reinterpret_cast<const int2 *>(v.htrace + (size_t)w * v.L * 4);
+        const int t1 = (1 >= v.hlen[w]) ? 0 : 1;
+        reinterpret_cast<int2 *>(v.hnx)[w] = *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + t1) * 4);
+    }
     if (lane < 6) v.counters[(size_t)w * 6 + lane] = 0;
 }
 
@@ -122,6 +129,10 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
     alloc((void **)&v.nstep, W * 4);
     alloc((void **)&v.err, W * 4);
     alloc((void **)&v.counters, W * 6 * 8);
+    alloc((void **)&v.hcur, W * 8);
+    alloc((void **)&v.hnx, W * 8);
+    alloc((void **)&e->d_work, 4);
+    alloc((void **)&e->d_work_bfs, 4);
     alloc((void **)&e->d_list, WN * 4);
     alloc((void **)&e->d_count, 4);
     if (err != cudaSuccess) { mapf_destroy(e); return cuda_fail(err, "mapf_create: cudaMalloc"); }
@@ -133,7 +144,7 @@ int mapf_destroy(MapfEnv *e) {
     if (!e) return MAPF_OK;
     EnvView &v = e->v;
     cudaFree(v.obst_bits); cudaFree(v.pos); cudaFree(v.goal); cudaFree(v.rep); cudaFree(v.qcur); cudaFree(v.htick);
-    cudaFree(v.tape_cur); cudaFree(v.nstep); cudaFree(v.err); cudaFree(v.counters); cudaFree(e->d_list); cudaFree(e->d_count);
+    cudaFree(v.tape_cur); cudaFree(v.nstep); cudaFree(v.err); cudaFree(v.counters); cudaFree(v.hcur); cudaFree(v.hnx); cudaFree(e->d_work); cudaFree(e->d_work_bfs); cudaFree(e->d_list); cudaFree(e->d_count);
     if (e->staging) {
         cudaFree(e->d_actions); cudaFree(e->d_out.status); cudaFree(e->d_out.reward); cudaFree(e->d_out.cost);
         cudaFree(e->d_out.train_valid); cudaFree(e->d_out.goals_reached); cudaFree(e->d_out.violated);
@@ -171,7 +182,7 @@ int mapf_evaluate(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, voi
     NEED_ENV("mapf_evaluate");
     if (!actions || !out) return fail(MAPF_E_NULL, "mapf_evaluate: null argument");
     if (int rc = check_step_n(e, "mapf_evaluate")) return rc;
-    CU(launch_step(e->v, actions, nullptr, *out, MODE_EVALUATE, (cudaStream_t)stream));
+    CU(launch_step(e->v, actions, nullptr, *out, MODE_EVALUATE, e->d_work, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -183,7 +194,7 @@ int mapf_joint_step(MapfEnv *e, const int8_t *actions, const int8_t *status, uin
     MapfStepOut o;
     memset(&o, 0, sizeof(o));
     o.goals_reached = goals_reached; o.violated = violated; o.fixed_actions = fixed_actions;
-    CU(launch_step(e->v, actions, status, o, MODE_JOINT, (cudaStream_t)stream));
+    CU(launch_step(e->v, actions, status, o, MODE_JOINT, e->d_work, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -191,14 +202,14 @@ int mapf_step(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, void *s
     NEED_ENV("mapf_step");
     if (!actions || !out) return fail(MAPF_E_NULL, "mapf_step: null argument");
     if (int rc = check_step_n(e, "mapf_step")) return rc;
-    CU(launch_step(e->v, actions, nullptr, *out, MODE_FUSED, (cudaStream_t)stream));
+    CU(launch_step(e->v, actions, nullptr, *out, MODE_FUSED, e->d_work, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
 int mapf_observe(MapfEnv *e, float *obs, float *vec, void *stream) {
     NEED_ENV("mapf_observe");
     if (!obs || !vec) return fail(MAPF_E_NULL, "mapf_observe: null argument");
-    CU(launch_observe(e->v, obs, vec, (cudaStream_t)stream));
+    CU(launch_observe(e->v, obs, vec, e->d_work, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -208,7 +219,7 @@ int mapf_bfs(MapfEnv *e, const int32_t *agent_list, int64_t n, int16_t *out, voi
     if (!agent_list) n = (int64_t)e->v.W * e->v.N;
     if (n < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_bfs: n < 0");
     if (n == 0) return MAPF_OK;
-    CU(launch_bfs(e->v, agent_list, n, nullptr, out, 0, (cudaStream_t)stream));
+    CU(launch_bfs(e->v, agent_list, n, nullptr, out, 0, e->d_work_bfs, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -216,7 +227,7 @@ int mapf_bfs_refresh(MapfEnv *e, const uint8_t *goals_reached, int16_t *bfs_maps
     NEED_ENV("mapf_bfs_refresh");
     if (!goals_reached || !bfs_maps) return fail(MAPF_E_NULL, "mapf_bfs_refresh: null argument");
     CU(launch_arrivals(e->v, goals_reached, e->d_list, e->d_count, (cudaStream_t)stream));
-    CU(launch_bfs(e->v, e->d_list, (long long)e->v.W * e->v.N, e->d_count, bfs_maps, 1, (cudaStream_t)stream));
+    CU(launch_bfs(e->v, e->d_list, (long long)e->v.W * e->v.N, e->d_count, bfs_maps, 1, e->d_work_bfs, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -249,7 +260,7 @@ int mapf_get_counters(MapfEnv *e, int64_t *counters, void *stream) {
 }
 
 int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfStepOutHost *out, float *obs_dev,
-                           float *vec_dev, float *obs_host, float *vec_host, void *stream) {
+                           float *vec_dev, float *train_valid_dev, float *obs_host, float *vec_host, void *stream) {
     NEED_ENV("mapf_step_observe_host");
     if (!actions_host || !out || !obs_dev || !vec_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host: null argument");
     if (int rc = check_step_n(e, "mapf_step_observe_host")) return rc;
@@ -273,13 +284,14 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
     if (!out->status) o.status = nullptr;
     if (!out->reward) o.reward = nullptr;
     if (!out->cost) o.cost = nullptr;
-    if (!out->train_valid) o.train_valid = nullptr;
+    if (train_valid_dev) o.train_valid = train_valid_dev;
+    else if (!out->train_valid) o.train_valid = nullptr;
     if (!out->goals_reached) o.goals_reached = nullptr;
     if (!out->violated) o.violated = nullptr;
     if (!out->shadow_goals) o.shadow_goals = nullptr;
     if (!out->fixed_actions) o.fixed_actions = nullptr;
-    CU(launch_step(v, e->d_actions, nullptr, o, MODE_FUSED, s));
-    CU(launch_observe(v, obs_dev, vec_dev, s));
+    CU(launch_step(v, e->d_actions, nullptr, o, MODE_FUSED, e->d_work, s));
+    CU(launch_observe(v, obs_dev, vec_dev, e->d_work, s));
     if (out->status) CU(cudaMemcpyAsync(out->status, o.status, WN, cudaMemcpyDeviceToHost, s));
     if (out->reward) CU(cudaMemcpyAsync(out->reward, o.reward, WN * 4, cudaMemcpyDeviceToHost, s));
     if (out->cost) CU(cudaMemcpyAsync(out->cost, o.cost, WN * 4, cudaMemcpyDeviceToHost, s));

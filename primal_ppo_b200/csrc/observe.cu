@@ -1,16 +1,19 @@
-// observe.cu — observation builder: one warp per world, persistent grid-stride loop over worlds.
+// observe.cu — observation builder: one warp per world, persistent CTAs with dynamic world scheduling.
 //
 // Replaces MapfGym.getAllObservations / observe / worldWithAgents (mapf_gym.py:192-198, 246-336) for W worlds:
 //   obs f32 [W,N,C,F,F]  (0/1 valued)   and   vec f32 [W,N,4] = [dx/d, dy/d, d, 0]
 // written straight into the policy's input tensors.  The store of obs is ~95 % of all bytes of a step, so the
-// kernel is organised around it:
-//   phase 1  lane = agent: build the agent's C*F*F observation as a BIT string in shared memory.  Channels 0/1 are
-//            F-bit windows cut out of padded obstacle / agent bit rows with one funnel shift per row (no per-cell
-//            work); channels 2-5 are a handful of single bits (own goal, clamped goals of visible agents, human).
+// kernel is organised around keeping 16-byte stores in flight:
+//   prefetch the NEXT world's inputs (agent cells, goals, obstacle bit rows, human tick) are loaded into registers
+//            while the current world is being written, and the index of the world after that is claimed with one
+//            atomicAdd per warp (dynamic scheduling: SMs that drain faster take more worlds, no tail).
+//   phase 1  lane = agent: build the agent's C*F*F observation as a BIT string.  Channels 0/1 are F-bit windows cut
+//            out of padded obstacle / agent-presence bit rows with one funnel shift per row (no per-cell work);
+//            channels 2-5 are a handful of single bits (own goal, clamped goals of visible agents, human).
 //   phase 1b compact the per-agent bit strings into one contiguous bit string of the chunk (N*C*F*F bits).
-//   phase 2  all 32 lanes expand bits to floats: 4 bits -> one 16-byte streaming store, 512 contiguous bytes per
-//            warp instruction, world after world (each world's block N*C*F*F*4 B is contiguous in HBM).
-// Algorithmic HBM traffic per world: write N*(4*C*F*F + 16) B, read N*8 B state + HP*RW*4 B obstacle bits + 8 B human.
+//   phase 2  all 32 lanes expand bits to floats: one nibble -> one 16-byte LUT read -> one 16-byte streaming store,
+//            512 contiguous bytes per warp instruction (each world's block N*C*F*F*4 B is contiguous in HBM).
+// Algorithmic HBM traffic per world: write N*(4*C*F*F + 16) B; read N*8 B state + HP*RW*4 B obstacle bits + 8 B human.
 #include "common.cuh"
 
 namespace mapf {
@@ -19,15 +22,19 @@ namespace {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+constexpr int OBW = 8;   // obstacle-bit words prefetched per lane (covers HP*RW <= 256; 144 for 40x40 with F=9)
+
 struct ObsLayout {
     int PB;      // bits per agent = C*F*F
     int AST;     // u32 stride of one agent's padded bit string (odd -> conflict-free lane-strided access)
     int CH;      // agents per chunk (<= 32)
     int WB;      // u32 words of the chunk bit string
+    int alias;   // 1: the chunk bit string overlays the staging area (single chunk per world)
+    int step_n, step_e;   // 1024 / PB, 1024 % PB: how (agent, bit) advances when the word index advances by 32
     size_t off_abits, off_grid, off_goal, off_aw, off_wb, total;
 };
 
-__host__ __device__ inline ObsLayout make_layout(int HP, int RW, int GS, int N, int C, int F, int CH) {
+inline ObsLayout make_layout(int HP, int RW, int GS, int N, int C, int F, int CH) {
     ObsLayout L;
     L.PB = C * F * F;
     int aw = (L.PB + 31) / 32 + 1;
@@ -35,12 +42,21 @@ __host__ __device__ inline ObsLayout make_layout(int HP, int RW, int GS, int N, 
     L.AST = aw;
     L.CH = CH;
     L.WB = (CH * L.PB + 31) / 32 + 2;
+    L.alias = (CH >= N) ? 1 : 0;
+    L.step_n = 1024 / L.PB;
+    L.step_e = 1024 % L.PB;
     size_t o = align16((size_t)HP * RW * 4);
     L.off_abits = o; o += align16((size_t)HP * RW * 4);
     L.off_grid = o; o += align16((size_t)HP * GS);
-    L.off_goal = o; o += align16((size_t)N * 4);
+    const size_t staging = o;
+    if (L.alias) {
+        L.off_wb = 0;
+        if (align16((size_t)L.WB * 4) > o) o = align16((size_t)L.WB * 4);
+    }
+    L.off_goal = o; o += align16((size_t)N * 8);      // goals [N] then cells [N]
     L.off_aw = o; o += align16((size_t)CH * L.AST * 4);
-    L.off_wb = o; o += align16((size_t)L.WB * 4);
+    if (!L.alias) { L.off_wb = o; o += align16((size_t)L.WB * 4); }
+    (void)staging;
     L.total = o;
     return L;
 }
@@ -52,71 +68,153 @@ __device__ __forceinline__ void or_bits(uint32_t *words, int p, uint32_t val, in
 }
 __device__ __forceinline__ void or_bit(uint32_t *words, int p) { words[p >> 5] |= 1u << (p & 31); }
 
-template <bool VEC4>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec, const ObsLayout L) {
+// inputs of one world held in registers (prefetched one world ahead)
+struct WorldRegs {
+    uint32_t pw, gw;        // cell / goal of agent `lane` (agents >= 32 are loaded directly)
+    uint32_t ob[OBW];       // obstacle bit words lane, lane+32, ...
+    int2 ht;                // human (pos, next) of the current tick
+};
+
+__device__ __forceinline__ void load_world(const EnvView &v, int w, int lane, int nob, WorldRegs &r) {
+    if (w < v.W) {
+        const size_t base = (size_t)w * v.N;
+        const int i = lane < v.N ? lane : 0;
+        r.pw = __ldg(reinterpret_cast<const uint32_t *>(v.pos) + base + i);
+        r.gw = __ldg(reinterpret_cast<const uint32_t *>(v.goal) + base + i);
+        const uint32_t *src = v.obst_bits + (size_t)w * nob;
+#pragma unroll
+        for (int k = 0; k < OBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? __ldg(src + k * 32 + lane) : 0u;
+        r.ht = __ldg(reinterpret_cast<const int2 *>(v.hcur) + w);
+    }
+}
+
+// C_T/F_T > 0: compile-time channels / FOV (the training configuration 6 x 9 x 9); 0: runtime values from EnvView.
+template <int C_T, int F_T, bool VEC4>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec, const ObsLayout L,
+               int *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint4 lut[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW, HP = v.HP, F = v.F, C = v.C, half = v.F >> 1;
-    const int FF = F * F, PB = L.PB, AST = L.AST, CH = L.CH;
+    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW, HP = v.HP;
+    const int F = F_T > 0 ? F_T : v.F, C = C_T > 0 ? C_T : v.C, half = F >> 1;
+    const int FF = F * F, PB = (C_T > 0 && F_T > 0) ? C_T * F_T * F_T : L.PB, AST = L.AST, CH = L.CH;
+    const int nob = HP * RW;
     unsigned char *base = smem_raw + (size_t)warp * L.total;
     uint32_t *obits = reinterpret_cast<uint32_t *>(base);
     uint32_t *abits = reinterpret_cast<uint32_t *>(base + L.off_abits);
     uint8_t *grid = base + L.off_grid;
     uint32_t *sgoal = reinterpret_cast<uint32_t *>(base + L.off_goal);
+    uint32_t *spos = sgoal + N;
     uint32_t *aw = reinterpret_cast<uint32_t *>(base + L.off_aw);
     uint32_t *wb = reinterpret_cast<uint32_t *>(base + L.off_wb);
 
-    // one-time clear of the agent bit rows and the id grid; every world un-scatters what it scattered
-    for (int k = lane; k < HP * RW; k += 32) abits[k] = 0;
-    {
-        uint4 *g4 = reinterpret_cast<uint4 *>(grid);
-        for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 16) {
+        const uint32_t one = 0x3f800000u, t = threadIdx.x;
+        lut[t] = make_uint4((t & 1u) ? one : 0u, (t & 2u) ? one : 0u, (t & 4u) ? one : 0u, (t & 8u) ? one : 0u);
     }
-    __syncwarp();
+    __syncthreads();
 
-    const int wpb = blockDim.x >> 5;
-    for (int w = blockIdx.x * wpb + warp; w < v.W; w += gridDim.x * wpb) {
-        // ---- stage: obstacle bit rows, agents (ids into the byte grid, presence into bit rows), goals -----------
-        {
-            const uint32_t *src = v.obst_bits + (size_t)w * HP * RW;
-            for (int k = lane; k < HP * RW; k += 32) obits[k] = __ldg(src + k);
+    // dynamic world scheduling, two indices ahead: w (inputs in registers), w1 (being loaded), w2 (being claimed)
+    int w, w1;
+    {
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(work_counter, 2);
+        t0 = __shfl_sync(FULL, t0, 0);
+        w = t0; w1 = t0 + 1;
+    }
+    WorldRegs cur, nxt;
+    load_world(v, w, lane, nob, cur);
+    const bool direct_ob = nob > OBW * 32;
+    bool first = true;
+
+    while (w < v.W) {
+        int w2 = 0;
+        if (lane == 0) w2 = atomicAdd(work_counter, 1);
+        load_world(v, w1, lane, nob, nxt);                       // in flight while this world is processed
+
+        // ---- stage: clean agent rows / id grid, obstacle bit rows from registers, agents, goals ---------------------
+        if (L.alias || first) {
+            for (int k = lane; k < nob; k += 32) abits[k] = 0;
+            uint4 *g4 = reinterpret_cast<uint4 *>(grid);
+            for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
+            first = false;
         }
+        if (!direct_ob) {
+#pragma unroll
+            for (int k = 0; k < OBW; ++k) if (k * 32 + lane < nob) obits[k * 32 + lane] = cur.ob[k];
+        } else {
+            const uint32_t *src = v.obst_bits + (size_t)w * nob;
+            for (int k = lane; k < nob; k += 32) obits[k] = __ldg(src + k);
+        }
+        __syncwarp();
         const uint32_t *posw = reinterpret_cast<const uint32_t *>(v.pos) + (size_t)w * N;
         const uint32_t *goalw = reinterpret_cast<const uint32_t *>(v.goal) + (size_t)w * N;
         for (int i = lane; i < N; i += 32) {
-            const uint32_t pw = __ldg(posw + i);
+            const uint32_t pw = i < 32 ? cur.pw : __ldg(posw + i);
             const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
             grid[(r + P) * GS + c + P] = (uint8_t)(i + 1);
             atomicOr(&abits[(r + P) * RW + ((c + P) >> 5)], 1u << ((c + P) & 31));
-            sgoal[i] = __ldg(goalw + i);
+            sgoal[i] = i < 32 ? cur.gw : __ldg(goalw + i);
+            spos[i] = pw;
         }
-        const int tick = v.htick[w];
-        const int2 ht = *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + tick) * 4);
-        const int nr = (int16_t)(ht.y & 0xffff), nc = (int16_t)((uint32_t)ht.y >> 16);   // human.getNextPos()
-        const int rows = v.dims ? v.dims[2 * w] : v.H, cols = v.dims ? v.dims[2 * w + 1] : v.Wd;
+        const int nr = (int16_t)(cur.ht.y & 0xffff), nc = (int16_t)((uint32_t)cur.ht.y >> 16);   // human.getNextPos()
+        int rows = v.H, cols = v.Wd;
+        if (v.use_da | v.use_hp) { if (v.dims) { rows = v.dims[2 * w]; cols = v.dims[2 * w + 1]; } }
         __syncwarp();
 
         for (int c0 = 0; c0 < N; c0 += CH) {
             const int nch = min(CH, N - c0);
             const int i = c0 + lane;
             const bool act = lane < nch;
-            // ---- phase 1: per-agent bit strings -------------------------------------------------------------
+            // ---- phase 1: per-agent bit strings -------------------------------------------------------------------
             if (act) {
                 uint32_t *my = aw + lane * AST;
-                for (int k = 0; k < AST; ++k) my[k] = 0;
-                const uint32_t pw = __ldg(posw + i), gw = sgoal[i];
+                const uint32_t pw = spos[i], gw = sgoal[i];
                 const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
                 const int gr = (int16_t)(gw & 0xffff), gc = (int16_t)(gw >> 16);
                 const int top = r - half, left = c - half;                                    // :251
+                const int off = left + P;
+                if (F_T > 0) {
+                    // channels 0 and 1 accumulate in registers at compile-time bit positions
+                    constexpr int FT = F_T > 0 ? F_T : 1;
+                    constexpr int NACC = (2 * FT * FT + 31) / 32 + 1;
+                    uint32_t acc[NACC];
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[k] = 0;
+#pragma unroll
+                    for (int y = 0; y < FT; ++y) {
+                        const int prow = top + y + P;
+                        uint32_t o = row_window(obits + prow * RW, off, FT);      // OOB or obstacle  (:270-276)
+                        uint32_t g = row_window(abits + prow * RW, off, FT);      // agents           (:278-285)
+                        if (y == FT / 2) { o |= 1u << (FT / 2); g &= ~(1u << (FT / 2)); }   // own cell -> channel 0 (:278-280)
+                        constexpr int dummy = 0; (void)dummy;
+                        const int p0 = y * FT, p1 = FT * FT + y * FT;
+                        acc[p0 >> 5] |= o << (p0 & 31);
+                        if ((p0 & 31) + FT > 32) acc[(p0 >> 5) + 1] |= o >> (32 - (p0 & 31));
+                        acc[p1 >> 5] |= g << (p1 & 31);
+                        if ((p1 & 31) + FT > 32) acc[(p1 >> 5) + 1] |= g >> (32 - (p1 & 31));
+                    }
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) my[k] = acc[k];
+                    for (int k = NACC; k < AST; ++k) my[k] = 0;
+                } else {
+                    for (int k = 0; k < AST; ++k) my[k] = 0;
+                    for (int y = 0; y < F; ++y) {
+                        const int prow = top + y + P;
+                        uint32_t o = row_window(obits + prow * RW, off, F);
+                        uint32_t g = row_window(abits + prow * RW, off, F);
+                        if (y == half) { o |= 1u << half; g &= ~(1u << half); }
+                        or_bits(my, y * F, o, F);
+                        or_bits(my, FF + y * F, g, F);
+                    }
+                }
+                // channel 3: goals of the agents visible in the window, clamped into it (:302-308)
                 for (int y = 0; y < F; ++y) {
-                    const int prow = top + y + P, off = left + P;
-                    uint32_t o = row_window(obits + prow * RW, off, F);      // OOB or obstacle  (:270-276)
-                    uint32_t g = row_window(abits + prow * RW, off, F);      // agents           (:278-285)
-                    if (y == half) { o |= 1u << half; g &= ~(1u << half); }  // own cell goes to channel 0 (:278-280)
-                    or_bits(my, y * F, o, F);
-                    or_bits(my, FF + y * F, g, F);
-                    while (g) {                                              // visible agents' goals, clamped (:302-308)
+                    const int prow = top + y + P;
+                    uint32_t g = row_window(abits + prow * RW, off, F);
+                    if (y == half) g &= ~(1u << half);
+                    while (g) {
                         const int x = __ffs(g) - 1; g &= g - 1;
                         const int j = grid[prow * GS + off + x] - 1;
                         const uint32_t jw = sgoal[j];
@@ -124,7 +222,9 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
                         const int mr = max(top, min(top + F - 1, jr)), mc = max(left, min(left + F - 1, jc));
                         or_bit(my, 3 * FF + (mr - top) * F + (mc - left));
                     }
-                    if (v.use_da) {                                          // danger disc |cell - H'| <= 5 (:289-290)
+                }
+                if (v.use_da) {                                              // danger disc |cell - H'| <= 5 (:289-290)
+                    for (int y = 0; y < F; ++y) {
                         const int rr = top + y, dy = rr > nr ? rr - nr : nr - rr;
                         if (rr >= 0 && rr < rows && dy <= 5) {
                             const int hw = dy == 0 ? 5 : dy <= 3 ? 4 : dy == 4 ? 3 : 0;
@@ -138,6 +238,7 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
                 if (nr >= top && nr < top + F && nc >= left && nc < left + F)                  // human (:310-312)
                     or_bit(my, 4 * FF + (nr - top) * F + (nc - left));
                 if (v.use_hp && C == 6 && v.hp5) {                                             // (:293-297)
+                    const int tick = v.htick[w];
                     const int16_t *p5 = v.hp5 + (v.hp5_per_tick ? ((size_t)w * v.L + tick) * 10 : (size_t)w * 10);
                     for (int k = 0; k < 5; ++k) {
                         const int pr = p5[2 * k], pc = p5[2 * k + 1];
@@ -156,84 +257,95 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
                 reinterpret_cast<float4 *>(vec)[(size_t)w * N + i] = o4;
             }
             __syncwarp();
-            // ---- phase 1b: compact to one contiguous bit string ------------------------------------------------
+            // ---- phase 1b: compact to one contiguous bit string (word m <- 32 bits starting at agent n, bit e) --------
             const int TB = nch * PB;
             const int nwords = (TB + 31) >> 5;
-            for (int m = lane; m < nwords; m += 32) {
-                const int b0 = m << 5;
-                const int n = b0 / PB, e = b0 - n * PB;
-                const uint32_t *src = aw + n * AST;
-                uint32_t x = __funnelshift_r(src[e >> 5], src[(e >> 5) + 1], e & 31);
-                const int valid = PB - e;
-                if (valid < 32) {
-                    x &= (1u << valid) - 1u;
-                    if (n + 1 < nch) x |= aw[(n + 1) * AST] << valid;
+            {
+                int n = (lane << 5) / PB, e = (lane << 5) - n * PB;
+                for (int m = lane; m < nwords; m += 32) {
+                    const uint32_t *src = aw + n * AST;
+                    uint32_t x = __funnelshift_r(src[e >> 5], src[(e >> 5) + 1], e & 31);
+                    const int valid = PB - e;
+                    if (valid < 32) {
+                        x &= (1u << valid) - 1u;
+                        if (n + 1 < nch) x |= aw[(n + 1) * AST] << valid;
+                    }
+                    wb[m] = x;
+                    n += L.step_n; e += L.step_e;
+                    if (e >= PB) { e -= PB; n += 1; }
                 }
-                wb[m] = x;
             }
             __syncwarp();
-            // ---- phase 2: bits -> floats, streaming stores -----------------------------------------------------
+            // ---- phase 2: bits -> floats, streaming stores ---------------------------------------------------------
             float *dst = obs + ((size_t)w * N + c0) * PB;
             if (VEC4) {
                 const int n4 = TB >> 2;
                 const int sh = (lane & 7) << 2;
                 const uint32_t *wp = wb + (lane >> 3);
                 float *d4 = dst + (lane << 2);
+#pragma unroll 4
                 for (int q = lane; q < n4; q += 32, wp += 4, d4 += 128) {
-                    const uint32_t nib = *wp >> sh;
-                    st_stream_v4(d4, (nib & 1u) ? 0x3f800000u : 0u, (nib & 2u) ? 0x3f800000u : 0u,
-                                 (nib & 4u) ? 0x3f800000u : 0u, (nib & 8u) ? 0x3f800000u : 0u);
+                    const uint4 val = lut[(*wp >> sh) & 15u];
+                    st_stream_v4(d4, val.x, val.y, val.z, val.w);
                 }
             } else {
                 for (int f = lane; f < TB; f += 32) dst[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 1.0f : 0.0f;
             }
             __syncwarp();
         }
-        // ---- un-scatter this world's agents so the next world starts from a clean grid ----------------------------
-        for (int i = lane; i < N; i += 32) {
-            const uint32_t pw = __ldg(posw + i);
-            const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
-            grid[(r + P) * GS + c + P] = 0;
-            abits[(r + P) * RW + ((c + P) >> 5)] = 0;
+        if (!L.alias) {
+            // un-scatter this world's agents so the next world starts from a clean grid
+            for (int i = lane; i < N; i += 32) {
+                const uint32_t pw = spos[i];
+                const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
+                grid[(r + P) * GS + c + P] = 0;
+                abits[(r + P) * RW + ((c + P) >> 5)] = 0;
+            }
         }
         __syncwarp();
+        w = w1;
+        w1 = __shfl_sync(FULL, w2, 0);
+        cur = nxt;
     }
+}
+
+template <int C_T, int F_T, bool VEC4>
+cudaError_t launch_t(const EnvView &v, float *obs, float *vec, const ObsLayout &L, int wpb, int *counter, cudaStream_t stream) {
+    const size_t smem = L.total * wpb;
+    cudaError_t e = cudaFuncSetAttribute(observe_kernel<C_T, F_T, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, observe_kernel<C_T, F_T, VEC4>, wpb * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int need = (v.W + wpb - 1) / wpb;
+    const int blocks = need < sms * per_sm ? need : sms * per_sm;
+    e = cudaMemsetAsync(counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    observe_kernel<C_T, F_T, VEC4><<<blocks, wpb * 32, smem, stream>>>(v, obs, vec, L, counter);
+    return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, cudaStream_t stream) {
+cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t stream) {
     const int PB = v.C * v.F * v.F;
     // chunk of agents handled per phase-1 pass: as many as fit ~24 KB of bit-string scratch per warp
     int CH = v.N < 32 ? v.N : 32;
     while (CH > 4 && (size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 24 * 1024) CH >>= 1;
-    const bool vec4 = ((size_t)v.N * PB) % 4 == 0 && (CH == v.N || ((size_t)CH * PB) % 4 == 0) &&
+    const bool vec4 = ((size_t)v.N * PB) % 4 == 0 && (CH >= v.N || ((size_t)CH * PB) % 4 == 0) &&
                       (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
     const ObsLayout L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
     int wpb = WARPS_PER_BLOCK;
     while (wpb > 1 && L.total * wpb > 200 * 1024) wpb >>= 1;
     if (L.total * wpb > 227 * 1024) return cudaErrorInvalidConfiguration;
-    const size_t smem = L.total * wpb;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e;
-    int per_sm = 1;
-    if (vec4) {
-        e = cudaFuncSetAttribute(observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, observe_kernel<true>, wpb * 32, smem);
-    } else {
-        e = cudaFuncSetAttribute(observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, observe_kernel<false>, wpb * 32, smem);
+    if (v.C == 6 && v.F == 9) {
+        return vec4 ? launch_t<6, 9, true>(v, obs, vec, L, wpb, work_counter, stream)
+                    : launch_t<6, 9, false>(v, obs, vec, L, wpb, work_counter, stream);
     }
-    if (per_sm < 1) per_sm = 1;
-    const int need = (v.W + wpb - 1) / wpb;
-    const int blocks = need < sms * per_sm ? need : sms * per_sm;
-    if (vec4) observe_kernel<true><<<blocks, wpb * 32, smem, stream>>>(v, obs, vec, L);
-    else observe_kernel<false><<<blocks, wpb * 32, smem, stream>>>(v, obs, vec, L);
-    return cudaGetLastError();
+    return vec4 ? launch_t<0, 0, true>(v, obs, vec, L, wpb, work_counter, stream)
+                : launch_t<0, 0, false>(v, obs, vec, L, wpb, work_counter, stream);
 }
 
 }  // namespace mapf

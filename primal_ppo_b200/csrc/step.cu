@@ -97,37 +97,54 @@ __device__ __forceinline__ void scan_diamond(const uint8_t *grid, int GS, int gr
     }
 }
 
+constexpr int SOBW = 5;   // obstacle-bit words prefetched per lane (HP*RW <= 160: 40x40 with F = 9 needs 144)
+
+// inputs of one world, prefetched one world ahead of the one being resolved
+struct StepRegs {
+    uint32_t pw, gw;          // cell, goal of agent `lane`
+    int rep, act;             // repetition action, joint action
+    int st_in;                // MODE_JOINT: status computed earlier by mapf_evaluate
+    uint32_t ob[SOBW];        // obstacle bit words lane, lane+32, ...
+    int2 ht, ht2;             // human (pos,next) at the current tick and after this step's tick
+    int tick, hlen;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *__restrict__ status_in,
-            const MapfStepOut out, const int per_warp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (w >= v.W) return;
-    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW, HP = v.HP;
-    WarpSmem s = carve(smem_raw + (size_t)warp * per_warp, HP, RW, GS);
+__device__ __forceinline__ void load_step_world(const EnvView &v, const int8_t *__restrict__ actions,
+                                                const int8_t *__restrict__ status_in, int w, int lane, int nob,
+                                                StepRegs &r) {
+    if (w < v.W) {
+        const size_t idx = (size_t)w * v.N + (lane < v.N ? lane : 0);
+        r.pw = reinterpret_cast<const uint32_t *>(v.pos)[idx];
+        r.gw = reinterpret_cast<const uint32_t *>(v.goal)[idx];
+        r.rep = v.rep[idx];
+        r.act = __ldg(actions + idx);
+        r.st_in = (MODE == MODE_JOINT) ? (int)__ldg(status_in + idx) : 0;
+        const uint32_t *src = v.obst_bits + (size_t)w * nob;
+#pragma unroll
+        for (int k = 0; k < SOBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? __ldg(src + k * 32 + lane) : 0u;
+        r.ht = reinterpret_cast<const int2 *>(v.hcur)[w];
+        r.ht2 = reinterpret_cast<const int2 *>(v.hnx)[w];
+        r.tick = v.htick[w];
+        r.hlen = __ldg(v.hlen + w);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOut &out, const WarpSmem &s, const int w,
+                                              const int lane, const StepRegs &in) {
+    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW;
     const bool active = lane < N;
     const size_t idx = (size_t)w * N + (active ? lane : 0);
-
-    // ---- stage the world: obstacle bit rows (HBM -> smem), zeroed agent-id grid -------------------------------
-    {
-        const uint32_t *src = v.obst_bits + (size_t)w * HP * RW;
-        for (int k = lane; k < HP * RW; k += 32) s.obits[k] = __ldg(src + k);
-        uint4 *g4 = reinterpret_cast<uint4 *>(s.grid);
-        for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
-    }
-    // ---- agent + human state ------------------------------------------------------------------------------
-    const uint32_t pw = reinterpret_cast<const uint32_t *>(v.pos)[idx];
-    const uint32_t gw = reinterpret_cast<const uint32_t *>(v.goal)[idx];
+    const uint32_t pw = in.pw, gw = in.gw;
     const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
     int goal_r = (int16_t)(gw & 0xffff), goal_c = (int16_t)(gw >> 16);
-    const int rep = v.rep[idx];
-    int a = actions[idx];
+    const int rep = in.rep;
+    int a = in.act;
     uint32_t errbits = 0;
     if (a < 0 || a >= NA) { if (active) errbits |= MAPF_ERR_BAD_ACTION; a = 0; }
-    const int tick = v.htick[w];
-    const int2 ht = *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + tick) * 4);
+    const int tick = in.tick;
+    const int2 ht = in.ht;
     const int hr = (int16_t)(ht.x & 0xffff), hc = (int16_t)((uint32_t)ht.x >> 16);
     const int nr = (int16_t)(ht.y & 0xffff), nc = (int16_t)((uint32_t)ht.y >> 16);
     __syncwarp();
@@ -162,7 +179,7 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
     // ---- status (getActionStatus :434-480) -----------------------------------------------------------------
     int st;
     if (MODE == MODE_JOINT) {
-        st = status_in[idx];
+        st = in.st_in;
     } else {
         const int cls = (inv0 & abit) ? C_INV0 : (inv1 & abit) ? C_INV1 : (good & abit) ? C_GOOD : C_E;
         st = cls == C_INV0 ? ST_STATIC : cls == C_INV1 ? ST_HUMAN : cls == C_GOOD ? ST_OK
@@ -226,6 +243,8 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
         if (MODE == MODE_EVALUATE) {
             const uint32_t eb = __reduce_or_sync(FULL, errbits);
             if (lane == 0 && eb) atomicOr(v.err + w, eb);
+            __syncwarp();
+            if (active) s.grid[gr * GS + gc] = 0;
             return;
         }
     }
@@ -317,8 +336,8 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
     // ---- moves, goal arrival, human tick, constraint violations (:620-633) ----------------------------------
     const int nr_ = r + dr_of(f), nc_ = c + dc_of(f);
     const bool arrived = active && nr_ == goal_r && nc_ == goal_c;
-    const int t2 = (tick + 1 >= v.hlen[w]) ? 0 : tick + 1;
-    const int2 ht2 = *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + t2) * 4);
+    const int t2 = (tick + 1 >= in.hlen) ? 0 : tick + 1;
+    const int2 ht2 = in.ht2;
     const int h2r = (int16_t)(ht2.x & 0xffff), h2c = (int16_t)((uint32_t)ht2.x >> 16);
     const bool viol = active && ((h2r - nr_) * (h2r - nr_) + (h2c - nc_) * (h2c - nc_) <= 24);   // cost_norm >= 0.01
     if (active) {
@@ -341,26 +360,82 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
     const uint32_t eb = __reduce_or_sync(FULL, errbits);
     if (lane == 0) {
         v.htick[w] = t2;
+        reinterpret_cast<int2 *>(v.hcur)[w] = ht2;
+        const int t3 = (t2 + 1 >= in.hlen) ? 0 : t2 + 1;          // keep the entry after next resident too
+        reinterpret_cast<int2 *>(v.hnx)[w] = *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + t3) * 4);
         v.nstep[w] += 1;
         if (eb) atomicOr(v.err + w, eb);
         long long *cn = v.counters + (size_t)w * 6;                              // util.py:56-65, runner.py:66-99
         cn[0] += __popc(am); cn[1] += __popc(sgm); cn[2] += __popc(c1); cn[3] += __popc(c2b); cn[4] += __popc(c3); cn[5] += __popc(vm_);
+    }
+    __syncwarp();
+    if (active) s.grid[gr * GS + gc] = 0;      // leave the id grid clean for the next world of this warp
+}
+
+// Persistent CTAs, one warp per world at a time; worlds are claimed with one atomicAdd per warp and the next world's
+// inputs are loaded into registers while the current one is being resolved.
+template <int MODE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *__restrict__ status_in,
+            const MapfStepOut out, const int per_warp, int *__restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HP = v.HP, RW = v.RW, GS = v.GS, nob = v.HP * v.RW;
+    WarpSmem s = carve(smem_raw + (size_t)warp * per_warp, HP, RW, GS);
+    {
+        uint4 *g4 = reinterpret_cast<uint4 *>(s.grid);
+        for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
+    }
+    int w, w1;
+    {
+        int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(work_counter, 2);
+        t0 = __shfl_sync(FULL, t0, 0);
+        w = t0; w1 = t0 + 1;
+    }
+    StepRegs cur, nxt;
+    load_step_world<MODE>(v, actions, status_in, w, lane, nob, cur);
+    const bool direct_ob = nob > SOBW * 32;
+    while (w < v.W) {
+        int w2 = 0;
+        if (lane == 0) w2 = atomicAdd(work_counter, 1);
+        load_step_world<MODE>(v, actions, status_in, w1, lane, nob, nxt);
+        if (!direct_ob) {
+#pragma unroll
+            for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < nob) s.obits[k * 32 + lane] = cur.ob[k];
+        } else {
+            const uint32_t *src = v.obst_bits + (size_t)w * nob;
+            for (int k = lane; k < nob; k += 32) s.obits[k] = __ldg(src + k);
+        }
+        resolve_world<MODE>(v, out, s, w, lane, cur);
+        __syncwarp();
+        w = w1;
+        w1 = __shfl_sync(FULL, w2, 0);
+        cur = nxt;
     }
 }
 
 }  // namespace
 
 cudaError_t launch_step(const EnvView &v, const int8_t *actions, const int8_t *status_in, const MapfStepOut &out,
-                        int mode, cudaStream_t stream) {
+                        int mode, int *work_counter, cudaStream_t stream) {
     const int per_warp = (int)warp_smem_bytes(v.HP, v.RW, v.GS);
     const size_t smem = (size_t)per_warp * WARPS_PER_BLOCK;
-    const int blocks = (v.W + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    const dim3 grid(blocks), block(WARPS_PER_BLOCK * 32);
-    cudaError_t e = cudaSuccess;
-#define LAUNCH(M)                                                                                            \
-    do {                                                                                                     \
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(step_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) step_kernel<M><<<grid, block, smem, stream>>>(v, actions, status_in, out, per_warp);  \
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int need = (v.W + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const dim3 block(WARPS_PER_BLOCK * 32);
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+#define LAUNCH(M)                                                                                                  \
+    do {                                                                                                           \
+        e = cudaFuncSetAttribute(step_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        int per_sm = 1;                                                                                            \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<M>, WARPS_PER_BLOCK * 32, smem); \
+        if (per_sm < 1) per_sm = 1;                                                                                \
+        const int blocks = need < sms * per_sm ? need : sms * per_sm;                                              \
+        if (e == cudaSuccess) step_kernel<M><<<blocks, block, smem, stream>>>(v, actions, status_in, out, per_warp, work_counter); \
     } while (0)
     if (mode == MODE_EVALUATE) LAUNCH(MODE_EVALUATE);
     else if (mode == MODE_JOINT) LAUNCH(MODE_JOINT);

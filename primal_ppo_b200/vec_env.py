@@ -229,39 +229,42 @@ class BatchedMapfGym:
         return c
 
     # ---- host-buffer step (what a CPU-side runner calls) ------------------------------------------------------------
-    def make_host_buffers(self, with_obs: bool = False):
-        """Pinned host buffers for ``step_observe_host``."""
+    def make_host_buffers(self, with_obs: bool = False, with_train_valid: bool = False):
+        """Pinned host buffers for ``step_observe_host``: the per-agent results the runner's bookkeeping reads on the
+        host (runner.py:66-99).  trainValid and the observations are training data consumed on the GPU; they are
+        mirrored to the host only on request."""
         W, N = self.W, self.N
         pin = dict(pin_memory=True)
         hb = dict(actions=torch.zeros((W, N), dtype=torch.int8, **pin),
                   status=torch.empty((W, N), dtype=torch.int8, **pin),
                   reward=torch.empty((W, N), dtype=torch.float32, **pin),
                   cost=torch.empty((W, N), dtype=torch.float32, **pin),
-                  train_valid=torch.empty((W, N, 5), dtype=torch.float32, **pin),
                   goals_reached=torch.empty((W, N), dtype=torch.uint8, **pin),
                   violated=torch.empty((W, N), dtype=torch.uint8, **pin),
                   shadow_goals=torch.empty((W,), dtype=torch.int32, **pin))
+        if with_train_valid:
+            hb["train_valid"] = torch.empty((W, N, 5), dtype=torch.float32, **pin)
         if with_obs:
             hb["obs"] = torch.empty((W, N, self.C, self.F, self.F), dtype=torch.float32, **pin)
             hb["vec"] = torch.empty((W, N, 4), dtype=torch.float32, **pin)
         return hb
 
-    def step_observe_host(self, hb: dict, obs_dev: torch.Tensor, vec_dev: torch.Tensor):
+    def step_observe_host(self, hb: dict, obs_dev: torch.Tensor, vec_dev: torch.Tensor,
+                          train_valid_dev: Optional[torch.Tensor] = None):
         """actions (host) -> H2D -> step -> observe -> results D2H, synchronised.  Returns bytes moved (h2d, d2h)."""
+        tvh = hb.get("train_valid")
         so = _cabi.MapfStepOutHost(status=hb["status"].data_ptr(), reward=hb["reward"].data_ptr(),
-                                   cost=hb["cost"].data_ptr(), train_valid=hb["train_valid"].data_ptr(),
+                                   cost=hb["cost"].data_ptr(), train_valid=None if tvh is None else tvh.data_ptr(),
                                    goals_reached=hb["goals_reached"].data_ptr(), violated=hb["violated"].data_ptr(),
                                    shadow_goals=hb["shadow_goals"].data_ptr(), fixed_actions=None)
         oh = hb.get("obs")
         vh = hb.get("vec")
+        tvd = self._out.train_valid if train_valid_dev is None else train_valid_dev
         _cabi.check(self._lib.mapf_step_observe_host(self._h, _ptr(hb["actions"]), C.byref(so), _ptr(obs_dev),
-                                                     _ptr(vec_dev), _ptr(oh), _ptr(vh), self._stream()),
+                                                     _ptr(vec_dev), _ptr(tvd), _ptr(oh), _ptr(vh), self._stream()),
                     "mapf_step_observe_host")
         h2d = hb["actions"].numel()
-        d2h = sum(hb[k].numel() * hb[k].element_size() for k in
-                  ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals"))
-        if oh is not None:
-            d2h += oh.numel() * 4 + vh.numel() * 4
+        d2h = sum(hb[k].numel() * hb[k].element_size() for k in hb if k != "actions")
         return h2d, d2h
 
 

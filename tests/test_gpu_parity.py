@@ -209,7 +209,7 @@ def test_gpu_host_buffer_call_equals_device_call():
     sc = random_scenario(512, 20, 20, 8, density=(0.1, 0.2), queue_len=4, seed=31, unique_maps=64)
     a = random_actions(6, 512, 8, seed=3)
     e1, e2 = _env(sc, use_tape=False), _env(sc, use_tape=False)
-    hb = e2.make_host_buffers(with_obs=True)
+    hb = e2.make_host_buffers(with_obs=True, with_train_valid=True)
     obs2 = torch.empty((512, 8, 6, 9, 9), device="cuda")
     vec2 = torch.empty((512, 8, 4), device="cuda")
     for t in range(6):
