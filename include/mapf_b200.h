@@ -51,7 +51,7 @@ typedef struct MapfConfig {
     int32_t num_worlds;   /* W */
     int32_t height;       /* H  (max rows over worlds) */
     int32_t width;        /* Wd (max cols over worlds) */
-    int32_t num_agents;   /* N  = EnvParameters.N_AGENTS  (alg_parameters.py:30); 1..32 for step, any for observe/bfs */
+    int32_t num_agents;   /* N  = EnvParameters.N_AGENTS  (alg_parameters.py:30); 1..128 for step, up to 254 for observe/bfs */
     int32_t fov;          /* F  = EnvParameters.FOV_SIZE  (alg_parameters.py:33); odd, 3..31 */
     int32_t num_channel;  /* C  = NetParameters.NUM_CHANNEL (alg_parameters.py:104); 5 or 6 */
     int32_t use_da;       /* FixedMapfGym(useDA=)  danger-area disc in channel 4   (mapf_gym.py:289-290) */
@@ -62,7 +62,8 @@ typedef struct MapfConfig {
     int32_t hp5_per_tick; /* 0: hp5 is [W,5,2]; 1: hp5 is [W,L,5,2] */
     uint64_t seed;        /* Philox key for the random branch of fixActions when no tape is given */
     int32_t device;       /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t world_offset; /* global index of this env's world 0 (rank r of a sharded job: r*W): keys the Philox draws so
+                             that world w behaves identically on whichever rank owns it */
 } MapfConfig;
 
 /* Exogenous inputs of a batch of worlds — what the reference draws from np.random / random at construction and on

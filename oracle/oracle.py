@@ -45,7 +45,7 @@ def _load():
         lib = C.CDLL(_LIB)
         p = C.c_void_p
         lib.orc_create.restype = p
-        lib.orc_create.argtypes = [C.c_int] * 10 + [p] * 6 + [C.c_int, p, p, C.c_int, p, C.c_uint64, C.c_int]
+        lib.orc_create.argtypes = [C.c_int] * 10 + [p] * 6 + [C.c_int, p, p, C.c_int, p, C.c_uint64, C.c_int, C.c_int]
         lib.orc_destroy.argtypes = [p]
         lib.orc_reset.argtypes = [p]
         lib.orc_get_action_status.argtypes = [p, p, p]
@@ -69,7 +69,7 @@ def _ptr(a):
 class OracleMapfGym:
     """Batched CPU oracle with the reference's method surface (leading world dim W)."""
 
-    def __init__(self, scenario, seed: int = 1234, threads: int = 1, use_tape: bool = True):
+    def __init__(self, scenario, seed: int = 1234, threads: int = 1, use_tape: bool = True, world_offset: int = 0):
         lib = _load()
         sc = scenario
         sc.validate()
@@ -84,7 +84,7 @@ class OracleMapfGym:
                                  int(sc.htrace.shape[1]), sc.fov, sc.num_channel, int(sc.use_da), int(sc.use_hp),
                                  *[_ptr(x) for x in self._keep[:6]],
                                  int(sc.hp5 is not None and sc.hp5.ndim == 4), _ptr(self._keep[6]), _ptr(self._keep[7]),
-                                 TL, _ptr(self._dims), C.c_uint64(seed), int(threads))
+                                 TL, _ptr(self._dims), C.c_uint64(seed), int(threads), int(world_offset))
         self._lib = lib
         lib.orc_reset(self._h)
 

@@ -21,7 +21,7 @@ class MapfConfig(C.Structure):
     _fields_ = [("num_worlds", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("num_agents", C.c_int32),
                 ("fov", C.c_int32), ("num_channel", C.c_int32), ("use_da", C.c_int32), ("use_hp", C.c_int32),
                 ("queue_len", C.c_int32), ("trace_len", C.c_int32), ("tape_stride", C.c_int32),
-                ("hp5_per_tick", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("hp5_per_tick", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("world_offset", C.c_int32)]
 
 
 class MapfScenario(C.Structure):

@@ -41,9 +41,7 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
     const long long n_maps = n_dev ? (long long)*n_dev : n_maps_in;   // device-side count: no host sync for refreshes
 
     for (;;) {
-        long long base = 0;
-        if (lane == 0) base = (long long)atomicAdd(work_counter, MPW);
-        base = __shfl_sync(FULL, base, 0);
+        const long long base = claim_work(work_counter, MPW, lane);
         if (base >= n_maps) break;
         const long long m = base + grp;
         const bool valid = m < n_maps;
@@ -144,6 +142,7 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
             __syncwarp();
         }
     }
+    finish_work(work_counter, gridDim.x * (blockDim.x >> 5), lane);
 }
 
 // Compaction of arrivals: flat ids (w*N+i) of agents with goals_reached == 1.  Order is irrelevant (each refreshed
@@ -184,8 +183,6 @@ cudaError_t launch_bfs_t(const EnvView &v, const int32_t *agent_list, long long 
     const long long need = (n + (long long)wpb * MPW - 1) / ((long long)wpb * MPW);
     const int blocks = (int)(need < (long long)sms * per_sm ? need : (long long)sms * per_sm);
     if (blocks <= 0) return cudaSuccess;
-    e = cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
-    if (e != cudaSuccess) return e;
     bfs_kernel<G, R, NW><<<blocks, wpb * 32, smem, stream>>>(v, agent_list, n, n_dev, out, tile_bytes, use_tma, scatter, work_counter);
     return cudaGetLastError();
 }

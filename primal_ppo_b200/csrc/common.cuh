@@ -31,6 +31,8 @@ struct EnvView {
     int HP;       // H + 2P
     int RW;       // u32 words per padded bit row (+1 spare word so a funnel read of word k+1 is always in range)
     int GS;       // byte stride of one row of the shared-memory agent-id grid (multiple of 16)
+    int dbg_flags; // experiment switches (MAPF_DBG_FLAGS), 0 in production
+    int world_offset; // global index of world 0 (sharded jobs): Philox counter = world_offset + w
     unsigned long long seed;
     // borrowed scenario
     const uint8_t *obst;
@@ -76,15 +78,65 @@ __device__ __forceinline__ uint32_t philox_draw(unsigned long long seed, uint32_
     return c0;
 }
 
+// L2 residency hints.  The env state (cells, goals, obstacle bit rows, human tick: ~55 MB for 65 536 worlds) is re-read
+// every step while 4 GB of observations stream through the same L2.  DRAM reads interleaved with the write stream cost
+// far more than their bytes (read/write bus turnarounds: measured -13 % write bandwidth for 1.6 % read bytes), so state
+// is loaded and stored with an evict_last policy and stays L2-resident across steps; observations are evict-first.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_keep(const void *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ld_keep_s8(const void *p, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.L2::cache_hint.s8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int2 ld_keep_v2(const void *p, uint64_t pol) {
+    int2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.b32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_keep(void *p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep_s8(void *p, int v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.b8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep_v2(void *p, int2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+
 // streaming 16-byte store: observations are written once and consumed by another kernel much later
 __device__ __forceinline__ void st_stream_v4(float *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Dynamic work distribution for the persistent kernels: counter[0] = next unit, counter[1] = warps that are done.
+// The last warp to finish re-arms the counter, so no memset node is needed between launches.
+__device__ __forceinline__ int claim_work(int *counter, int n, int lane) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(counter, n);
+    return __shfl_sync(FULL, t, 0);
+}
+__device__ __forceinline__ void finish_work(int *counter, int total_warps, int lane) {
+    if (lane == 0) {
+        const int d = atomicAdd(counter + 1, 1);
+        if (d == total_warps - 1) { counter[0] = 0; counter[1] = 0; }
+    }
 }
 
 // launchers implemented in the .cu files
 cudaError_t launch_reset(const EnvView &v, cudaStream_t s);
 cudaError_t launch_step(const EnvView &v, const int8_t *actions, const int8_t *status_in, const MapfStepOut &out,
                         int mode, int *work_counter, cudaStream_t s);
+cudaError_t launch_step_wide(const EnvView &v, const int8_t *actions, const int8_t *status_in, const MapfStepOut &out,
+                             int mode, cudaStream_t s);
 cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t s);
 cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
                        int scatter, int *work_counter, cudaStream_t s);

@@ -1,6 +1,7 @@
 // mapf_api.cu — the C ABI declared in include/mapf_b200.h (handle, reset, argument checking, host-buffer calls).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -111,7 +112,7 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
     EnvView &v = e->v;
     v.W = c.num_worlds; v.H = c.height; v.Wd = c.width; v.N = c.num_agents; v.F = c.fov; v.C = c.num_channel;
     v.use_da = c.use_da; v.use_hp = c.use_hp; v.Q = c.queue_len; v.L = c.trace_len; v.TL = c.tape_stride;
-    v.hp5_per_tick = c.hp5_per_tick; v.seed = c.seed;
+    v.hp5_per_tick = c.hp5_per_tick; v.seed = c.seed; v.world_offset = c.world_offset;
     v.P = c.fov / 2 > 2 ? c.fov / 2 : 2;
     v.HP = v.H + 2 * v.P;
     v.RW = (v.Wd + 2 * v.P + 31) / 32 + 1;
@@ -131,11 +132,14 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
     alloc((void **)&v.counters, W * 6 * 8);
     alloc((void **)&v.hcur, W * 8);
     alloc((void **)&v.hnx, W * 8);
-    alloc((void **)&e->d_work, 4);
-    alloc((void **)&e->d_work_bfs, 4);
+    alloc((void **)&e->d_work, 8);
+    alloc((void **)&e->d_work_bfs, 8);
     alloc((void **)&e->d_list, WN * 4);
     alloc((void **)&e->d_count, 4);
     if (err != cudaSuccess) { mapf_destroy(e); return cuda_fail(err, "mapf_create: cudaMalloc"); }
+    cudaMemset(e->d_work, 0, 8);
+    cudaMemset(e->d_work_bfs, 0, 8);
+    if (const char *f = getenv("MAPF_DBG_FLAGS")) v.dbg_flags = atoi(f);
     *out = e;
     return MAPF_OK;
 }
@@ -174,15 +178,20 @@ int mapf_reset(MapfEnv *e, const MapfScenario *sc, void *stream) {
     if (!e->has_scenario) return fail(MAPF_E_STATE, name ": mapf_reset has not been called")
 
 static int check_step_n(const MapfEnv *e, const char *name) {
-    if (e->v.N > 32) return fail(MAPF_E_UNSUPPORTED, "%s: joint-step resolution supports N <= 32 agents per world (got %d)", name, e->v.N);
+    if (e->v.N > 128) return fail(MAPF_E_UNSUPPORTED, "%s: joint-step resolution supports N <= 128 agents per world (got %d)", name, e->v.N);
     return MAPF_OK;
+}
+// N <= 32: lane = agent (step.cu); 32 < N <= 128: lane loops over agents (step_wide.cu)
+static cudaError_t do_step(MapfEnv *e, const int8_t *actions, const int8_t *status, const MapfStepOut &o, int mode, cudaStream_t s) {
+    if (e->v.N <= 32) return launch_step(e->v, actions, status, o, mode, e->d_work, s);
+    return launch_step_wide(e->v, actions, status, o, mode, s);
 }
 
 int mapf_evaluate(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, void *stream) {
     NEED_ENV("mapf_evaluate");
     if (!actions || !out) return fail(MAPF_E_NULL, "mapf_evaluate: null argument");
     if (int rc = check_step_n(e, "mapf_evaluate")) return rc;
-    CU(launch_step(e->v, actions, nullptr, *out, MODE_EVALUATE, e->d_work, (cudaStream_t)stream));
+    CU(do_step(e, actions, nullptr, *out, MODE_EVALUATE, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -194,7 +203,7 @@ int mapf_joint_step(MapfEnv *e, const int8_t *actions, const int8_t *status, uin
     MapfStepOut o;
     memset(&o, 0, sizeof(o));
     o.goals_reached = goals_reached; o.violated = violated; o.fixed_actions = fixed_actions;
-    CU(launch_step(e->v, actions, status, o, MODE_JOINT, e->d_work, (cudaStream_t)stream));
+    CU(do_step(e, actions, status, o, MODE_JOINT, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -202,7 +211,7 @@ int mapf_step(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, void *s
     NEED_ENV("mapf_step");
     if (!actions || !out) return fail(MAPF_E_NULL, "mapf_step: null argument");
     if (int rc = check_step_n(e, "mapf_step")) return rc;
-    CU(launch_step(e->v, actions, nullptr, *out, MODE_FUSED, e->d_work, (cudaStream_t)stream));
+    CU(do_step(e, actions, nullptr, *out, MODE_FUSED, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -290,7 +299,7 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
     if (!out->violated) o.violated = nullptr;
     if (!out->shadow_goals) o.shadow_goals = nullptr;
     if (!out->fixed_actions) o.fixed_actions = nullptr;
-    CU(launch_step(v, e->d_actions, nullptr, o, MODE_FUSED, e->d_work, s));
+    CU(do_step(e, e->d_actions, nullptr, o, MODE_FUSED, s));
     CU(launch_observe(v, obs_dev, vec_dev, e->d_work, s));
     if (out->status) CU(cudaMemcpyAsync(out->status, o.status, WN, cudaMemcpyDeviceToHost, s));
     if (out->reward) CU(cudaMemcpyAsync(out->reward, o.reward, WN * 4, cudaMemcpyDeviceToHost, s));

@@ -75,16 +75,16 @@ struct WorldRegs {
     int2 ht;                // human (pos, next) of the current tick
 };
 
-__device__ __forceinline__ void load_world(const EnvView &v, int w, int lane, int nob, WorldRegs &r) {
+__device__ __forceinline__ void load_world(const EnvView &v, int w, int lane, int nob, uint64_t pol, WorldRegs &r) {
     if (w < v.W) {
         const size_t base = (size_t)w * v.N;
         const int i = lane < v.N ? lane : 0;
-        r.pw = __ldg(reinterpret_cast<const uint32_t *>(v.pos) + base + i);
-        r.gw = __ldg(reinterpret_cast<const uint32_t *>(v.goal) + base + i);
+        r.pw = ld_keep(reinterpret_cast<const uint32_t *>(v.pos) + base + i, pol);
+        r.gw = ld_keep(reinterpret_cast<const uint32_t *>(v.goal) + base + i, pol);
         const uint32_t *src = v.obst_bits + (size_t)w * nob;
 #pragma unroll
-        for (int k = 0; k < OBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? __ldg(src + k * 32 + lane) : 0u;
-        r.ht = __ldg(reinterpret_cast<const int2 *>(v.hcur) + w);
+        for (int k = 0; k < OBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? ld_keep(src + k * 32 + lane, pol) : 0u;
+        r.ht = ld_keep_v2(reinterpret_cast<const int2 *>(v.hcur) + w, pol);
     }
 }
 
@@ -116,22 +116,17 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
     __syncthreads();
 
     // dynamic world scheduling, two indices ahead: w (inputs in registers), w1 (being loaded), w2 (being claimed)
-    int w, w1;
-    {
-        int t0 = 0;
-        if (lane == 0) t0 = atomicAdd(work_counter, 2);
-        t0 = __shfl_sync(FULL, t0, 0);
-        w = t0; w1 = t0 + 1;
-    }
+    int w = claim_work(work_counter, 2, lane), w1 = w + 1;
+    const uint64_t pol = policy_evict_last();
     WorldRegs cur, nxt;
-    load_world(v, w, lane, nob, cur);
+    load_world(v, w, lane, nob, pol, cur);
     const bool direct_ob = nob > OBW * 32;
     bool first = true;
 
     while (w < v.W) {
         int w2 = 0;
         if (lane == 0) w2 = atomicAdd(work_counter, 1);
-        load_world(v, w1, lane, nob, nxt);                       // in flight while this world is processed
+        load_world(v, w1, lane, nob, pol, nxt);                  // in flight while this world is processed
 
         // ---- stage: clean agent rows / id grid, obstacle bit rows from registers, agents, goals ---------------------
         if (L.alias || first) {
@@ -307,6 +302,7 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
         w1 = __shfl_sync(FULL, w2, 0);
         cur = nxt;
     }
+    finish_work(work_counter, gridDim.x * (blockDim.x >> 5), lane);
 }
 
 template <int C_T, int F_T, bool VEC4>
@@ -321,8 +317,6 @@ cudaError_t launch_t(const EnvView &v, float *obs, float *vec, const ObsLayout &
     if (per_sm < 1) per_sm = 1;
     const int need = (v.W + wpb - 1) / wpb;
     const int blocks = need < sms * per_sm ? need : sms * per_sm;
-    e = cudaMemsetAsync(counter, 0, sizeof(int), stream);
-    if (e != cudaSuccess) return e;
     observe_kernel<C_T, F_T, VEC4><<<blocks, wpb * 32, smem, stream>>>(v, obs, vec, L, counter);
     return cudaGetLastError();
 }

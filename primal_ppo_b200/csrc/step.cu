@@ -18,13 +18,12 @@
 // anything); the remaining queue is processed in the reference's FIFO order, each iteration executed by the lane
 // that owns the agent, with the committed actions in shared memory.
 #include "common.cuh"
+#include "step_common.cuh"
 
 namespace mapf {
 
 namespace {
 
-constexpr int C_INV0 = 0, C_INV1 = 1, C_GOOD = 2, C_E = 3;
-constexpr int FIX_CAP = 256;  // fixActions iteration cap (reference: unbounded while loop, mapf_gym.py:563); same in the oracle
 constexpr int QRING = 64;     // problemAgents ring: an agent is queued at most once at a time, so <= 32 live entries
 
 struct WarpSmem {
@@ -61,42 +60,6 @@ __device__ inline WarpSmem carve(unsigned char *base, int HP, int RW, int GS) {
     return s;
 }
 
-// Scan the radius-2 diamond around (gr, gc) [padded grid coordinates] for other agents.
-//   restr  : bit a set iff another agent lies within Manhattan distance 1 of T(a)
-//   confl  : bit a set iff some neighbour j with b = other_act[j] >= 0 has conflict(i,a; j,b)
-//   selmask: agents j (bitmask) with conflict(i, a_sel; j, other_act[j])
-__device__ __forceinline__ void scan_diamond(const uint8_t *grid, int GS, int gr, int gc, int self_code,
-                                             const int8_t *other_act, int a_sel, uint32_t &restr, uint32_t &confl,
-                                             uint32_t &selmask) {
-    restr = 0; confl = 0; selmask = 0;
-#pragma unroll
-    for (int dr = -2; dr <= 2; ++dr) {
-#pragma unroll
-        for (int dc = -2; dc <= 2; ++dc) {
-            const int md = (dr < 0 ? -dr : dr) + (dc < 0 ? -dc : dc);
-            if (md == 0 || md > 2) continue;
-            const int code = grid[(gr + dr) * GS + (gc + dc)];
-            if (code == 0 || code == self_code) continue;
-            const int j = code - 1;
-            const int b = other_act[j];
-            const int tr = dr + (b >= 0 ? dr_of(b) : 0), tc = dc + (b >= 0 ? dc_of(b) : 0);  // T_j - pos_i
-#pragma unroll
-            for (int a = 0; a < NA; ++a) {
-                const int ar = (a == 2) - (a == 4), ac = (a == 1) - (a == 3);
-                const int d1 = (dr - ar < 0 ? ar - dr : dr - ar) + (dc - ac < 0 ? ac - dc : dc - ac);
-                if (d1 > 1) continue;                       // compile-time: j not adjacent to T_i(a)
-                restr |= 1u << a;
-                bool c = (b >= 0) && (tr == ar) && (tc == ac);                                    // vertex
-                if (a != 0 && dr == ar && dc == ac) c = c || (b == (a == 1 ? 3 : a == 2 ? 4 : a == 3 ? 1 : 2));  // swap
-                if (c) {
-                    confl |= 1u << a;
-                    if (a == a_sel) selmask |= 1u << j;
-                }
-            }
-        }
-    }
-}
-
 constexpr int SOBW = 5;   // obstacle-bit words prefetched per lane (HP*RW <= 160: 40x40 with F = 9 needs 144)
 
 // inputs of one world, prefetched one world ahead of the one being resolved
@@ -112,27 +75,27 @@ struct StepRegs {
 template <int MODE>
 __device__ __forceinline__ void load_step_world(const EnvView &v, const int8_t *__restrict__ actions,
                                                 const int8_t *__restrict__ status_in, int w, int lane, int nob,
-                                                StepRegs &r) {
+                                                uint64_t pol, StepRegs &r) {
     if (w < v.W) {
         const size_t idx = (size_t)w * v.N + (lane < v.N ? lane : 0);
-        r.pw = reinterpret_cast<const uint32_t *>(v.pos)[idx];
-        r.gw = reinterpret_cast<const uint32_t *>(v.goal)[idx];
-        r.rep = v.rep[idx];
+        r.pw = ld_keep(reinterpret_cast<const uint32_t *>(v.pos) + idx, pol);
+        r.gw = ld_keep(reinterpret_cast<const uint32_t *>(v.goal) + idx, pol);
+        r.rep = ld_keep_s8(v.rep + idx, pol);
         r.act = __ldg(actions + idx);
         r.st_in = (MODE == MODE_JOINT) ? (int)__ldg(status_in + idx) : 0;
         const uint32_t *src = v.obst_bits + (size_t)w * nob;
 #pragma unroll
-        for (int k = 0; k < SOBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? __ldg(src + k * 32 + lane) : 0u;
-        r.ht = reinterpret_cast<const int2 *>(v.hcur)[w];
-        r.ht2 = reinterpret_cast<const int2 *>(v.hnx)[w];
-        r.tick = v.htick[w];
+        for (int k = 0; k < SOBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? ld_keep(src + k * 32 + lane, pol) : 0u;
+        r.ht = ld_keep_v2(reinterpret_cast<const int2 *>(v.hcur) + w, pol);
+        r.ht2 = ld_keep_v2(reinterpret_cast<const int2 *>(v.hnx) + w, pol);
+        r.tick = (int)ld_keep(v.htick + w, pol);
         r.hlen = __ldg(v.hlen + w);
     }
 }
 
 template <int MODE>
 __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOut &out, const WarpSmem &s, const int w,
-                                              const int lane, const StepRegs &in) {
+                                              const int lane, const StepRegs &in, const uint64_t pol) {
     const int N = v.N, P = v.P, GS = v.GS, RW = v.RW;
     const bool active = lane < N;
     const size_t idx = (size_t)w * N + (active ? lane : 0);
@@ -170,7 +133,7 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
         if (hv && !(inv0 >> k & 1)) inv1 |= 1u << k;
     }
     uint32_t restr, confl, mmask;
-    scan_diamond(s.grid, GS, gr, gc, lane + 1, s.act, a, restr, confl, mmask);
+    scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.act, a, restr, confl, mmask);
     const uint32_t repbit = rep >= 0 ? (1u << rep) : 0u;
     const uint32_t good = ~(inv0 | inv1 | restr | repbit) & 31u;
     const uint32_t abit = 1u << a;
@@ -271,7 +234,7 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
                 if (lane == k) {
                     const uint32_t viable = ~(inv0 | inv1) & 31u;                 // :575
                     uint32_t r2, c2, m2;
-                    scan_diamond(s.grid, GS, gr, gc, lane + 1, s.commit, -1, r2, c2, m2);
+                    scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, -1, r2, c2, m2);
                     const uint32_t ok = viable & ~(restr & c2);                   // :577-584
                     int choice;
                     if (good) {
@@ -293,7 +256,7 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
                                 choice = tp[cur];
                                 const int ne = tp[cur + 1];
                                 if (choice < 0 || choice >= NA) { errbits |= MAPF_ERR_TAPE; choice = __ffs(viable) - 1; }
-                                scan_diamond(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
+                                scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
                                 uint32_t seen = 0;
                                 for (int q = 0; q < ne && cur + 2 + q < tl; ++q) {
                                     const int j = tp[cur + 2 + q];
@@ -309,11 +272,11 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
                             }
                             v.tape_cur[w] = cur;
                         } else {                                                  // Philox stand-in, ascending eviction
-                            int pick = (int)(philox_draw(v.seed, (uint32_t)w, (uint32_t)v.nstep[w], draw) % (uint32_t)nv);
+                            int pick = (int)(philox_draw(v.seed, (uint32_t)(w + v.world_offset), (uint32_t)v.nstep[w], draw) % (uint32_t)nv);
                             uint32_t vm = viable;
                             while (pick--) vm &= vm - 1;
                             choice = __ffs(vm) - 1;
-                            scan_diamond(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
+                            scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
                         }
                         draw++;
                         while (ev) {                                              // :593-596
@@ -341,13 +304,13 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
     const int h2r = (int16_t)(ht2.x & 0xffff), h2c = (int16_t)((uint32_t)ht2.x >> 16);
     const bool viol = active && ((h2r - nr_) * (h2r - nr_) + (h2c - nc_) * (h2c - nc_) <= 24);   // cost_norm >= 0.01
     if (active) {
-        reinterpret_cast<uint32_t *>(v.pos)[idx] = (uint32_t)(uint16_t)nr_ | ((uint32_t)(uint16_t)nc_ << 16);
-        v.rep[idx] = (int8_t)opp_of(f);                                          // takeStep :158-161
+        st_keep(reinterpret_cast<uint32_t *>(v.pos) + idx, (uint32_t)(uint16_t)nr_ | ((uint32_t)(uint16_t)nc_ << 16), pol);
+        st_keep_s8(v.rep + idx, opp_of(f), pol);                                 // takeStep :158-161
         if (arrived) {                                                           // Sequence.getNext util.py:33-39
             int k = v.qcur[idx];
             if (k >= v.Q) k = v.Q - 1; else v.qcur[idx] = k + 1;
-            reinterpret_cast<uint32_t *>(v.goal)[idx] =
-                reinterpret_cast<const uint32_t *>(v.goal_queue)[idx * v.Q + k];
+            st_keep(reinterpret_cast<uint32_t *>(v.goal) + idx,
+                    reinterpret_cast<const uint32_t *>(v.goal_queue)[idx * v.Q + k], pol);
         }
         if (out.goals_reached) out.goals_reached[idx] = arrived;
         if (out.violated) out.violated[idx] = viol;
@@ -359,10 +322,10 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
                    c3 = __ballot_sync(FULL, active && st == ST_AGENT);
     const uint32_t eb = __reduce_or_sync(FULL, errbits);
     if (lane == 0) {
-        v.htick[w] = t2;
-        reinterpret_cast<int2 *>(v.hcur)[w] = ht2;
+        st_keep(v.htick + w, (uint32_t)t2, pol);
+        st_keep_v2(reinterpret_cast<int2 *>(v.hcur) + w, ht2, pol);
         const int t3 = (t2 + 1 >= in.hlen) ? 0 : t2 + 1;          // keep the entry after next resident too
-        reinterpret_cast<int2 *>(v.hnx)[w] = *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + t3) * 4);
+        st_keep_v2(reinterpret_cast<int2 *>(v.hnx) + w, *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + t3) * 4), pol);
         v.nstep[w] += 1;
         if (eb) atomicOr(v.err + w, eb);
         long long *cn = v.counters + (size_t)w * 6;                              // util.py:56-65, runner.py:66-99
@@ -386,20 +349,15 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
         uint4 *g4 = reinterpret_cast<uint4 *>(s.grid);
         for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
     }
-    int w, w1;
-    {
-        int t0 = 0;
-        if (lane == 0) t0 = atomicAdd(work_counter, 2);
-        t0 = __shfl_sync(FULL, t0, 0);
-        w = t0; w1 = t0 + 1;
-    }
+    int w = claim_work(work_counter, 2, lane), w1 = w + 1;
+    const uint64_t pol = policy_evict_last();
     StepRegs cur, nxt;
-    load_step_world<MODE>(v, actions, status_in, w, lane, nob, cur);
+    load_step_world<MODE>(v, actions, status_in, w, lane, nob, pol, cur);
     const bool direct_ob = nob > SOBW * 32;
     while (w < v.W) {
         int w2 = 0;
         if (lane == 0) w2 = atomicAdd(work_counter, 1);
-        load_step_world<MODE>(v, actions, status_in, w1, lane, nob, nxt);
+        load_step_world<MODE>(v, actions, status_in, w1, lane, nob, pol, nxt);
         if (!direct_ob) {
 #pragma unroll
             for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < nob) s.obits[k * 32 + lane] = cur.ob[k];
@@ -407,12 +365,13 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
             const uint32_t *src = v.obst_bits + (size_t)w * nob;
             for (int k = lane; k < nob; k += 32) s.obits[k] = __ldg(src + k);
         }
-        resolve_world<MODE>(v, out, s, w, lane, cur);
+        resolve_world<MODE>(v, out, s, w, lane, cur, pol);
         __syncwarp();
         w = w1;
         w1 = __shfl_sync(FULL, w2, 0);
         cur = nxt;
     }
+    finish_work(work_counter, gridDim.x * (blockDim.x >> 5), lane);
 }
 
 }  // namespace
@@ -426,8 +385,7 @@ cudaError_t launch_step(const EnvView &v, const int8_t *actions, const int8_t *s
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int need = (v.W + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const dim3 block(WARPS_PER_BLOCK * 32);
-    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
 #define LAUNCH(M)                                                                                                  \
     do {                                                                                                           \
         e = cudaFuncSetAttribute(step_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \

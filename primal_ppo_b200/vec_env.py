@@ -48,7 +48,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class BatchedMapfGym:
-    def __init__(self, scenario: Scenario, device=None, seed: int = 1234, use_tape: bool = True):
+    def __init__(self, scenario: Scenario, device=None, seed: int = 1234, use_tape: bool = True,
+                 world_offset: int = 0):
         if not torch.cuda.is_available():
             raise _cabi.MapfError("BatchedMapfGym needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._lib = _cabi.load_library()
@@ -71,7 +72,7 @@ class BatchedMapfGym:
                                queue_len=int(sc.goal_queue.shape[2]), trace_len=int(sc.htrace.shape[1]),
                                tape_stride=0 if tape is None else int(tape.shape[1]),
                                hp5_per_tick=int(sc.hp5 is not None and sc.hp5.ndim == 4), seed=seed,
-                               device=self.device.index or 0, reserved=0)
+                               device=self.device.index or 0, world_offset=int(world_offset))
         h = C.c_void_p()
         _cabi.check(self._lib.mapf_create(C.byref(cfg), C.byref(h)), "mapf_create")
         self._h = h

@@ -150,9 +150,33 @@ def test_gpu_eval_channels_and_large_fov_observe_only():
         assert torch.equal(vec, torch.from_numpy(o_vec).cuda()), fov
         if fov == 9:
             _eq(_np(env.bfs_maps()), orc.bfs_maps(), "bfs 80x80")
-            from primal_ppo_b200._cabi import MapfError
-            with pytest.raises(MapfError):
-                env.step(torch.zeros((6, 128), dtype=torch.int8))
+
+
+def test_gpu_matches_oracle_config5_shape_80x80x128():
+    """BASELINE.json configs[4] shape: 80x80 worlds, 128 agents (the lane-loops-over-agents step kernel)."""
+    sc = random_scenario(48, 80, 80, 128, density=(0.0, 0.3), queue_len=4, seed=51, unique_maps=12)
+    _run_vs_oracle(sc, T=24, check_obs_every=4)
+    sc = random_scenario(64, 16, 16, 48, density=(0.1, 0.25), queue_len=4, seed=52, unique_maps=16)   # crowded, N = 48
+    _run_vs_oracle(sc, T=32, check_obs_every=4)
+
+
+def test_gpu_sharded_worlds_equal_unsharded():
+    """World w gives the same bits whichever rank owns it: run worlds [0,W) in one env and as two shards
+    (world_offset keys the Philox draws), compare every output."""
+    sc = random_scenario(512, 8, 8, 8, density=(0.2, 0.3), queue_len=6, seed=61, unique_maps=64)
+    acts = random_actions(32, 512, 8, seed=62)
+    full = _env(sc, use_tape=False, seed=77)
+    lo = _env(sc.slice(0, 200), use_tape=False, seed=77, world_offset=0)
+    hi = _env(sc.slice(200, 512), use_tape=False, seed=77, world_offset=200)
+    for t in range(32):
+        a = torch.from_numpy(acts[t]).cuda()
+        o = full.step(a); o1 = lo.step(a[:200]); o2 = hi.step(a[200:])
+        for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "fixed_actions"):
+            assert torch.equal(getattr(o, key), torch.cat([getattr(o1, key), getattr(o2, key)])), (t, key)
+        obs, vec = full.getAllObservations()
+        ob1, _ = lo.getAllObservations(); ob2, _ = hi.getAllObservations()
+        assert torch.equal(obs, torch.cat([ob1, ob2]))
+    assert torch.equal(full.state()["err"], torch.cat([lo.state()["err"], hi.state()["err"]]))
 
 
 def test_gpu_bfs_refresh_in_place():

@@ -1,0 +1,238 @@
+// Micro-benchmark: how fast can a write-only kernel stream 4 GB to HBM on B200 under different access patterns?
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/wpb tools/write_pattern_bench.cu && /tmp/wpb
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__device__ __forceinline__ void st_cs(float *p, uint4 v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// A: every warp owns contiguous chunks of `chunk` bytes, claimed dynamically (the observe kernel's pattern)
+template <bool CS>
+__global__ void warp_chunks(float *out, int nchunks, int chunk_f4, int *counter) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(counter, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= nchunks) break;
+        float *dst = out + (size_t)c * chunk_f4 * 4 + lane * 4;
+        const uint4 v = make_uint4(c, lane, 0x3f800000u, 0);
+#pragma unroll 4
+        for (int q = lane; q < chunk_f4; q += 32, dst += 128) {
+            if (CS) st_cs(dst, v); else *reinterpret_cast<uint4 *>(dst) = v;
+        }
+    }
+}
+// B: a block of 8 warps owns 8 consecutive chunks and writes them cooperatively (4 KB contiguous per block step)
+template <bool CS>
+__global__ void block_chunks(float *out, int nchunks, int chunk_f4, int *counter) {
+    __shared__ int sc;
+    for (;;) {
+        if (threadIdx.x == 0) sc = atomicAdd(counter, 8);
+        __syncthreads();
+        const int c = sc;
+        __syncthreads();
+        if (c >= nchunks) break;
+        const int total = chunk_f4 * 8;
+        float *dst = out + (size_t)c * chunk_f4 * 4;
+        const uint4 v = make_uint4(c, threadIdx.x, 0x3f800000u, 0);
+        for (int q = threadIdx.x; q < total; q += blockDim.x) {
+            if (CS) st_cs(dst + (size_t)q * 4, v); else *reinterpret_cast<uint4 *>(dst + (size_t)q * 4) = v;
+        }
+    }
+}
+// D: pattern A + the observe kernel's inner loop (bit word from smem -> 16-entry LUT in smem -> store), with `smem_pad`
+//    bytes of dynamic shared memory per block to mimic its carve-out
+template <bool LUT, int READS = 0>
+__global__ void __launch_bounds__(256, 4) warp_chunks_lut(float *out, int nchunks, int chunk_f4, int *counter,
+                                                          const uint32_t *__restrict__ in = nullptr) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ uint4 lut[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wb = reinterpret_cast<uint32_t *>(dyn) + warp * 512;
+    if (threadIdx.x < 16) {
+        const uint32_t one = 0x3f800000u, t = threadIdx.x;
+        lut[t] = make_uint4((t & 1u) ? one : 0u, (t & 2u) ? one : 0u, (t & 4u) ? one : 0u, (t & 8u) ? one : 0u);
+    }
+    for (int k = lane; k < 512; k += 32) wb[k] = 0x01020304u * (k + 1 + warp);
+    __syncthreads();
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(counter, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= nchunks) break;
+        float *dst = out + (size_t)c * chunk_f4 * 4 + lane * 4;
+        const int sh = (lane & 7) << 2;
+        const uint32_t *wp = wb + (lane >> 3);
+        uint32_t acc = 0;
+        if (READS > 0) {
+#pragma unroll
+            for (int k = 0; k < READS; ++k) acc += __ldg(in + ((size_t)c * READS + k) * 32 + lane);
+            if (acc == 0x12345678u) wb[lane] = acc;     // keep the loads alive
+        }
+#pragma unroll 4
+        for (int q = lane; q < chunk_f4; q += 32, dst += 128, wp += 4) {
+            const uint32_t nb = *wp >> sh;
+            uint4 v;
+            if (LUT) v = lut[nb & 15u];
+            else v = make_uint4((nb & 1u) * 0x3f800000u, (nb & 2u) * 0x1fc00000u, (nb & 4u) * 0x0fe00000u, (nb & 8u) * 0x07f00000u);
+            *reinterpret_cast<uint4 *>(dst) = v;
+        }
+    }
+}
+// F: D + READS x 128 B of reads per chunk, issued one chunk AHEAD (software prefetch, like the observe kernel)
+__device__ __forceinline__ uint32_t ld_pol(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+// POL: 0 plain loads / plain stores, 1 evict_last loads + .cs stores, 2 evict_last loads + evict_first-hinted stores
+template <int READS, int POL = 0>
+__global__ void __launch_bounds__(256, 4) warp_chunks_prefetch(float *out, int nchunks, int chunk_f4, int *counter,
+                                                               const uint32_t *__restrict__ in, size_t in_mask = ~(size_t)0) {
+    uint64_t pol_last, pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ uint4 lut[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wb = reinterpret_cast<uint32_t *>(dyn) + warp * 512;
+    if (threadIdx.x < 16) {
+        const uint32_t one = 0x3f800000u, t = threadIdx.x;
+        lut[t] = make_uint4((t & 1u) ? one : 0u, (t & 2u) ? one : 0u, (t & 4u) ? one : 0u, (t & 8u) ? one : 0u);
+    }
+    for (int k = lane; k < 512; k += 32) wb[k] = 0x01020304u * (k + 1 + warp);
+    __syncthreads();
+    int c = 0, c1 = 0;
+    if (lane == 0) c = atomicAdd(counter, 2);
+    c = __shfl_sync(0xffffffffu, c, 0); c1 = c + 1;
+    uint32_t cur[READS], nxt[READS];
+#pragma unroll
+    for (int k = 0; k < READS; ++k) cur[k] = c < nchunks ? (POL ? ld_pol(in + ((((size_t)c * READS + k) * 32) & in_mask) + lane, pol_last) : __ldg(in + ((((size_t)c * READS + k) * 32) & in_mask) + lane)) : 0;
+    while (c < nchunks) {
+        int c2 = 0;
+        if (lane == 0) c2 = atomicAdd(counter, 1);
+#pragma unroll
+        for (int k = 0; k < READS; ++k) nxt[k] = c1 < nchunks ? (POL ? ld_pol(in + ((((size_t)c1 * READS + k) * 32) & in_mask) + lane, pol_last) : __ldg(in + ((((size_t)c1 * READS + k) * 32) & in_mask) + lane)) : 0;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < READS; ++k) acc += cur[k];
+        wb[lane] = acc | 0x01020304u;
+        __syncwarp();
+        float *dst = out + (size_t)c * chunk_f4 * 4 + lane * 4;
+        const int sh = (lane & 7) << 2;
+        const uint32_t *wp = wb + (lane >> 3);
+#pragma unroll 4
+        for (int q = lane; q < chunk_f4; q += 32, dst += 128, wp += 4) {
+            const uint4 v = lut[(*wp >> sh) & 15u];
+            if (POL == 1) st_cs(dst, v);
+            else if (POL == 2) asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol_first) : "memory");
+            else *reinterpret_cast<uint4 *>(dst) = v;
+        }
+        __syncwarp();
+        c = c1; c1 = __shfl_sync(0xffffffffu, c2, 0);
+#pragma unroll
+        for (int k = 0; k < READS; ++k) cur[k] = nxt[k];
+    }
+}
+// C: plain grid-stride fill
+__global__ void fill(float *out, size_t n4) {
+    const uint4 v = make_uint4(1, 2, 3, 4);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4 *>(out)[i] = v;
+}
+
+int main() {
+    const int nchunks = 65536, chunk_f4 = 62208 / 16;
+    const size_t bytes = (size_t)nchunks * 62208;
+    float *out; int *counter;
+    cudaMalloc(&out, bytes); cudaMalloc(&counter, 4);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    auto run = [&](const char *name, auto launch) {
+        float best = 1e9;
+        for (int it = 0; it < 6; ++it) {
+            cudaMemset(counter, 0, 4);
+            cudaEventRecord(a); launch(); cudaEventRecord(b); cudaEventSynchronize(b);
+            float ms; cudaEventElapsedTime(&ms, a, b); if (it > 0 && ms < best) best = ms;
+        }
+        printf("%-44s %.3f ms  %.0f GB/s  (%s)\n", name, best, bytes / (best * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
+    };
+    for (int bps : {2, 3, 4, 6, 8}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "A warp chunks .cs, %d blocks/SM x 8 warps", bps);
+        run(nm, [&] { warp_chunks<true><<<148 * bps, 256>>>(out, nchunks, chunk_f4, counter); });
+        snprintf(nm, sizeof nm, "A warp chunks default, %d blocks/SM x 8 warps", bps);
+        run(nm, [&] { warp_chunks<false><<<148 * bps, 256>>>(out, nchunks, chunk_f4, counter); });
+    }
+    for (int bps : {2, 4, 8}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "B block chunks default, %d blocks/SM", bps);
+        run(nm, [&] { block_chunks<false><<<148 * bps, 256>>>(out, nchunks, chunk_f4, counter); });
+        snprintf(nm, sizeof nm, "B block chunks .cs, %d blocks/SM", bps);
+        run(nm, [&] { block_chunks<true><<<148 * bps, 256>>>(out, nchunks, chunk_f4, counter); });
+    }
+    for (int pad : {16384, 47104}) {
+        char nm[96];
+        cudaFuncSetAttribute(warp_chunks_lut<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        cudaFuncSetAttribute(warp_chunks_lut<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        for (int bps : {2, 4}) {
+            snprintf(nm, sizeof nm, "D warp chunks + smem word + LUT, %d blk/SM, %d B smem", bps, pad);
+            run(nm, [&] { warp_chunks_lut<true><<<148 * bps, 256, pad>>>(out, nchunks, chunk_f4, counter); });
+            snprintf(nm, sizeof nm, "D warp chunks + smem word + ALU, %d blk/SM, %d B smem", bps, pad);
+            run(nm, [&] { warp_chunks_lut<false><<<148 * bps, 256, pad>>>(out, nchunks, chunk_f4, counter); });
+        }
+    }
+    {
+        uint32_t *in; cudaMalloc(&in, (size_t)nchunks * 8 * 128); cudaMemset(in, 1, (size_t)nchunks * 8 * 128);
+        cudaFuncSetAttribute(warp_chunks_lut<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 47104);
+        run("E = D(LUT, 4 blk/SM, 46 KB) + 8 x 128 B reads per chunk", [&] { warp_chunks_lut<true, 8><<<148 * 4, 256, 47104>>>(out, nchunks, chunk_f4, counter, in); });
+        cudaFuncSetAttribute(warp_chunks_lut<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 47104);
+        run("E = D(LUT, 4 blk/SM, 46 KB) + 2 x 128 B reads per chunk", [&] { warp_chunks_lut<true, 2><<<148 * 4, 256, 47104>>>(out, nchunks, chunk_f4, counter, in); });
+    }
+    {
+        const size_t in_bytes = (size_t)nchunks * 7 * 128;     // 58.7 MB, like the env state of 65 536 worlds
+        uint32_t *in; cudaMalloc(&in, in_bytes); cudaMemset(in, 1, in_bytes);
+        const int sm = 47104;
+        cudaFuncSetAttribute(warp_chunks_prefetch<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(warp_chunks_prefetch<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(warp_chunks_prefetch<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        run("F0 7 prefetched reads/chunk, plain", [&] { warp_chunks_prefetch<7, 0><<<148 * 4, 256, sm>>>(out, nchunks, chunk_f4, counter, in); });
+        run("F3 same but reads always hit (1 KB region)", [&] { warp_chunks_prefetch<7, 0><<<148 * 4, 256, sm>>>(out, nchunks, chunk_f4, counter, in, (size_t)255); });
+        run("F1 evict_last loads + .cs stores", [&] { warp_chunks_prefetch<7, 1><<<148 * 4, 256, sm>>>(out, nchunks, chunk_f4, counter, in); });
+        run("F2 evict_last loads + evict_first stores", [&] { warp_chunks_prefetch<7, 2><<<148 * 4, 256, sm>>>(out, nchunks, chunk_f4, counter, in); });
+        // persisting-L2 access policy window over the input region
+        cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+        printf("persistingL2CacheMaxSize %.1f MB, accessPolicyMaxWindowSize %.1f MB, L2 %.1f MB\n", prop.persistingL2CacheMaxSize / 1e6,
+               prop.accessPolicyMaxWindowSize / 1e6, prop.l2CacheSize / 1e6);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize);
+        cudaStream_t st; cudaStreamCreate(&st);
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.base_ptr = in;
+        attr.accessPolicyWindow.num_bytes = in_bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        auto runs = [&](const char *name, auto launch) {
+            float best = 1e9;
+            for (int it = 0; it < 6; ++it) {
+                cudaMemsetAsync(counter, 0, 4, st);
+                cudaEventRecord(a, st); launch(); cudaEventRecord(b, st); cudaEventSynchronize(b);
+                float ms; cudaEventElapsedTime(&ms, a, b); if (it > 0 && ms < best) best = ms;
+            }
+            printf("%-44s %.3f ms  %.0f GB/s  (%s)\n", name, best, bytes / (best * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
+        };
+        runs("F4 persisting window on inputs, plain ld/st", [&] { warp_chunks_prefetch<7, 0><<<148 * 4, 256, sm, st>>>(out, nchunks, chunk_f4, counter, in); });
+        runs("F5 persisting window + .cs stores", [&] { warp_chunks_prefetch<7, 1><<<148 * 4, 256, sm, st>>>(out, nchunks, chunk_f4, counter, in); });
+    }
+    for (int bps : {4, 8, 16}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "C grid-stride fill, %d blocks/SM", bps);
+        run(nm, [&] { fill<<<148 * bps, 256>>>(out, bytes / 16); });
+    }
+    cudaMemset(out, 0, bytes); cudaDeviceSynchronize();
+    run("cudaMemset", [&] { cudaMemsetAsync(out, 0, bytes); });
+    return 0;
+}
