@@ -114,13 +114,11 @@ def cpu_port_throughput(budget_s, worlds, threads, seed=7):
     sc = build_scenario(worlds, seed)
     env = OracleMapfGym(sc, seed=1234, threads=threads, use_tape=False)
     acts = random_actions(16, worlds, N_AGENTS, seed=seed)
-    out = env.getAllObservations()
-    env.step(acts[0]); env.getAllObservations(out=out)          # warm-up
+    bufs = env.step_observe(acts[0])                            # warm-up
     t0 = time.perf_counter()
     steps = 0
     while True:
-        env.step(acts[steps % 16])
-        env.getAllObservations(out=out)
+        env.step_observe(acts[steps % 16], bufs)
         steps += 1
         if time.perf_counter() - t0 >= budget_s:
             break
@@ -133,8 +131,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import max_threads
-    threads = min(max_threads(), len(os.sched_getaffinity(0)))
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle takes the count explicitly)
+    threads = len(os.sched_getaffinity(0))
     worlds = 32 * threads
     from oracle import OracleMapfGym, build_oracle
     from primal_ppo_b200 import random_actions
@@ -142,16 +140,16 @@ def run_reference(args):
     sc = build_scenario(worlds, 7)
     env = OracleMapfGym(sc, seed=1234, threads=threads, use_tape=False)
     acts = random_actions(16, worlds, N_AGENTS, seed=7)
-    out = env.getAllObservations()
+    bufs = env.step_observe(acts[0])
     # each bench "step" is a bounded sample: `inner` env steps over `worlds` worlds
-    inner = 8
+    inner = 64
     for w in range(args.warmup):
         for k in range(inner):
-            env.step(acts[k % 16]); env.getAllObservations(out=out)
+            env.step_observe(acts[k % 16], bufs)
     t0 = time.perf_counter()
     for s in range(args.steps):
         for k in range(inner):
-            env.step(acts[k % 16]); env.getAllObservations(out=out)
+            env.step_observe(acts[k % 16], bufs)
     dt = time.perf_counter() - t0
     value = worlds * N_AGENTS * inner * args.steps / dt
     sample = f"{worlds} worlds 40x40x32 agents x {inner} env steps per bench step, {threads} OpenMP threads"
@@ -318,8 +316,7 @@ def main():
         achieved = obs_bytes / (obs_ms * 1e-3) / 1e9
         cpu = None
         if world_size == 1 and args.cpu_budget > 0:
-            from oracle.oracle import max_threads
-            threads = min(max_threads(), len(os.sched_getaffinity(0)))
+            threads = len(os.sched_getaffinity(0))
             cw = 32 * threads
             cv, csteps, cdt = cpu_port_throughput(args.cpu_budget, cw, threads)
             cpu = {"value": cv, "unit": "agent-steps/s", "cores": threads, "kind": "port",

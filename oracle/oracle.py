@@ -55,6 +55,7 @@ def _load():
         lib.orc_joint_step.argtypes = [p, p, p, p, p, p]
         lib.orc_get_all_observations.argtypes = [p, p, p]
         lib.orc_bfs.argtypes = [p, p]
+        lib.orc_step_observe.argtypes = [p] * 12
         lib.orc_state.argtypes = [p, p, p, p, p, p]
         lib.orc_gae.argtypes = [p, p, p, C.c_double, C.c_double, C.c_int, C.c_int, p, p]
         lib.orc_max_threads.restype = C.c_int
@@ -169,6 +170,22 @@ class OracleMapfGym:
         rw[g == 1] += GOAL_REWARD
         return dict(status=st, reward=rw, cost=cost, train_valid=tv, goals_reached=g, violated=v, shadow=sg,
                     fixed=self.fixed_actions)
+
+
+    def step_observe(self, actions, bufs=None):
+        """One fused CPU call per env step (five calls + goal bonus + getAllObservations), one OpenMP region."""
+        a = self._acts(actions)
+        if bufs is None:
+            W, N = self.W, self.N
+            bufs = dict(status=np.empty((W, N), np.int8), reward=np.empty((W, N), np.float32),
+                        cost=np.empty((W, N), np.float32), train_valid=np.empty((W, N, 5), np.float32),
+                        goals_reached=np.empty((W, N), np.uint8), violated=np.empty((W, N), np.uint8),
+                        shadow=np.empty((W,), np.int32), fixed=np.empty((W, N), np.int8),
+                        obs=np.empty((W, N, self.Cn, self.F, self.F), np.float32), vec=np.empty((W, N, 4), np.float32))
+        self._lib.orc_step_observe(self._h, _ptr(a), *[_ptr(bufs[k]) for k in
+                                   ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow",
+                                    "fixed", "obs", "vec")])
+        return bufs
 
 
 def gae_oracle(rewards, values, last_values, gamma=0.95, lam=0.95):

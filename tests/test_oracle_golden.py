@@ -45,3 +45,16 @@ def test_oracle_gae_matches_reference_runner():
     np.testing.assert_array_equal(ret.view(np.uint32), d["returns"].view(np.uint32))
     cret, _ = gae_oracle(d["cost_rewards"], d["cost_values"], d["last_cost_values"], float(d["gamma"]), float(d["lam"]))
     np.testing.assert_array_equal(cret.view(np.uint32), d["cost_returns"].view(np.uint32))
+
+
+def test_oracle_fused_step_observe_equals_separate_calls():
+    g = Golden("g_8x8_n8_dense")
+    e1, e2 = OracleMapfGym(g.scenario, threads=2), OracleMapfGym(g.scenario, threads=3)
+    for t in range(g.T):
+        a = e1.step(g["actions"][t])
+        o1, v1 = e1.getAllObservations()
+        b = e2.step_observe(g["actions"][t])
+        for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow", "fixed"):
+            np.testing.assert_array_equal(a[key], b[key], err_msg=f"t={t} {key}")
+        np.testing.assert_array_equal(o1, b["obs"])
+        np.testing.assert_array_equal(v1.view(np.uint32), b["vec"].view(np.uint32))
