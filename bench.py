@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one joint step (mapf_step) + one observation build (mapf_observe) over all worlds of the rank:
+One "step" = one joint step + one observation build over all worlds of the rank (mapf_step_observe, one launch):
 the rollout loop's per-step env work (runner.py:64-100) with the policy excluded.
 Workload (N=1) = BASELINE.json configs[2]: 65 536 lockstep 40x40 worlds, 32 agents, obstacle density U[0,0.3],
 uniform random actions.  Weak scaling: every rank owns 65 536 worlds; worlds never communicate.
@@ -35,11 +35,24 @@ FOV, CH = 9, 6
 
 
 def algorithmic_bytes(n_agents=N_AGENTS, h=H, wd=WD, c=CH, f=FOV):
-    """SURVEY.md §8d, per agent-step: step ~ 46 + (H*Wd+8)/N, observe ~ 16 + 4*C*F^2 + (H*Wd+8)/N + 8."""
+    """SURVEY.md §8d, per agent-step: step ~ 46 + (H*Wd+8)/N, observe ~ 16 + 4*C*F^2 + (H*Wd+8)/N + 8, and for the
+    fused step+observe launch B = 62 + 4*C*F^2 + (H*Wd+8)/N (the world's map and human are read once)."""
     shared = (h * wd + 8) / n_agents
     step = 46 + shared
     observe = 16 + 4 * c * f * f + shared + 8
-    return step, observe
+    fused = 62 + 4 * c * f * f + shared
+    return step, observe, fused
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on this workload, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_traffic.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -209,31 +222,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident throughput (value) + per-kernel CUDA-event timings -----------------------
+    # ---------------- device-resident throughput (value): one fused step+observe launch per step ------------------
     for i in range(Wu):
-        env.step(ring[i % 8]); env.getAllObservations(out=(obs, vec))
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        env.step_observe(ring[i % 8], obs_out=(obs, vec))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     barrier()
     with ClockSampler(local_rank) as clk:
         t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
         t_start.record()
         for i in range(K):
             ev[i][0].record()
-            env.step(ring[i % 8])
+            env.step_observe(ring[i % 8], obs_out=(obs, vec))
             ev[i][1].record()
-            env.getAllObservations(out=(obs, vec))
-            ev[i][2].record()
         t_end.record()
         barrier()
     total_ms = t_start.elapsed_time(t_end)
-    step_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    obs_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    fused_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max = float(tmax.item())
     value = Wn * N * K * world_size / (total_ms_max * 1e-3)
     err_frac = float((env.state()["err"] != 0).float().mean())
+
+    # ---------------- the same work as two launches (mapf_step, mapf_observe): per-kernel CUDA-event timings ------
+    Kk = max(3, min(K, 20))
+    evk = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(Kk)]
+    for i in range(3):
+        env.step(ring[i % 8]); env.getAllObservations(out=(obs, vec))
+    torch.cuda.synchronize(dev)
+    for i in range(Kk):
+        evk[i][0].record()
+        env.step(ring[i % 8])
+        evk[i][1].record()
+        env.getAllObservations(out=(obs, vec))
+        evk[i][2].record()
+    torch.cuda.synchronize(dev)
+    step_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evk]))
+    obs_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evk]))
 
     # ---------------- end to end through the host-buffer C-ABI call ---------------------------------------------
     hb = env.make_host_buffers(with_obs=False)
@@ -310,10 +336,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        b_step, b_obs = algorithmic_bytes()
+        b_step, b_obs, b_fused = algorithmic_bytes()
         obs_bytes = b_obs * Wn * N
         step_bytes = b_step * Wn * N
-        achieved = obs_bytes / (obs_ms * 1e-3) / 1e9
+        fused_bytes = b_fused * Wn * N
+        achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
         cpu = None
         if world_size == 1 and args.cpu_budget > 0:
             threads = len(os.sched_getaffinity(0))
@@ -326,6 +353,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16 state, f32 obs", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "worlds_per_gpu": Wn, "agents": N, "grid": [H, WD], "fov": FOV,
                            "channels": CH, "actions": "uniform random, device-resident ring of 8",
+                           "call": "mapf_step_observe (one fused launch per step)",
                            "l2": "working set per step (obs 4.08 GB/GPU written) far exceeds the 126 MB L2; no flush needed",
                            "worlds_with_error_flags": err_frac},
                 "clocks": clk.summary(),
@@ -334,15 +362,23 @@ def main():
                                              "(status, reward, cost, goals, violations, shadow goals) copied back to pinned host "
                                              "memory every step; observations and trainValid stay in HBM as the policy's / learner's "
                                              "input tensors"},
-                "gpu_launches": 2 * K,
-                "roofline": {"bound": "hbm", "kernel": "observe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": obs_bytes, "ms_per_launch": obs_ms},
-                "kernels": {"step_kernel": {"ms": step_ms, "algorithmic_bytes": step_bytes,
+                "gpu_launches": K,
+                "roofline": {"bound": "hbm", "kernel": "step_observe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": ncu_traffic("step_observe_kernel"), "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms,
+                             "algorithmic_bytes_per_agent_step": b_fused},
+                "kernels": {"step_observe_kernel": {"ms": fused_ms, "algorithmic_bytes": fused_bytes, "achieved_gbs": achieved,
+                                                    "frac": achieved / peak, "traffic": ncu_traffic("step_observe_kernel")},
+                            "step_kernel": {"ms": step_ms, "algorithmic_bytes": step_bytes,
                                             "achieved_gbs": step_bytes / (step_ms * 1e-3) / 1e9,
-                                            "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
-                            "observe_kernel": {"ms": obs_ms, "algorithmic_bytes": obs_bytes, "achieved_gbs": achieved,
-                                               "frac": achieved / peak}},
+                                            "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                                            "traffic": ncu_traffic("step_kernel")},
+                            "observe_kernel": {"ms": obs_ms, "algorithmic_bytes": obs_bytes,
+                                               "achieved_gbs": obs_bytes / (obs_ms * 1e-3) / 1e9,
+                                               "frac": obs_bytes / (obs_ms * 1e-3) / 1e9 / peak,
+                                               "traffic": ncu_traffic("observe_kernel")},
+                            "note": "step_kernel / observe_kernel: the same work as two launches (mapf_step, mapf_observe), "
+                                    "timed in a separate loop of %d steps" % Kk},
                 "cpu_baseline": cpu}
         line.update(line_extra)
         print(json.dumps(line), flush=True)

@@ -118,6 +118,12 @@ int mapf_step(MapfEnv *env, const int8_t *actions, const MapfStepOut *out, void 
 /* getAllObservations (mapf_gym.py:327-336): obs f32 [W,N,C,F,F], vec f32 [W,N,4], written in place. */
 int mapf_observe(MapfEnv *env, float *obs, float *vec, void *stream);
 
+/* One env step of the rollout loop in ONE launch (runner.py:64-100): mapf_step followed by mapf_observe of the new
+ * state, fused per world so that the step resolution hides under the observation stores.  Bit-identical to calling
+ * the two entry points back to back (which is what happens for shapes the fused kernel does not cover: N > 32 or an
+ * observation block that needs several chunks). */
+int mapf_step_observe(MapfEnv *env, const int8_t *actions, const MapfStepOut *out, float *obs, float *vec, void *stream);
+
 /* makeBfsMap (mapf_gym.py:211-244) for the CURRENT goals.  agent_list: n flat ids (w*N+i), or NULL for all W*N
  * agents in order.  out: int16 [n,H,Wd]: -1 obstacle (and cells outside a world's dims), -2 unreached, >=0 distance. */
 int mapf_bfs(MapfEnv *env, const int32_t *agent_list, int64_t n, int16_t *out, void *stream);

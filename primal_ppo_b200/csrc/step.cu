@@ -19,321 +19,13 @@
 // that owns the agent, with the committed actions in shared memory.
 #include "common.cuh"
 #include "step_common.cuh"
+#include "step_world.cuh"
 
 namespace mapf {
 
 namespace {
 
-constexpr int QRING = 64;     // problemAgents ring: an agent is queued at most once at a time, so <= 32 live entries
-
-struct WarpSmem {
-    uint32_t *obits;   // [HP*RW]
-    uint8_t *grid;     // [HP*GS] agent id + 1, 0 = none
-    float *tv;         // [32*5]
-    uint32_t *mmask;   // [32] agents in conflict with my chosen action
-    int8_t *act;       // [32] sanitised joint action
-    int8_t *cls;       // [32]
-    int8_t *st;        // [32]
-    int8_t *commit;    // [32] agentActionPairs[:,1]
-    int8_t *rep;       // [32]
-    int8_t *queue;     // [QRING] problemAgents (ring buffer)
-};
-
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
-__host__ __device__ inline size_t warp_smem_bytes(int HP, int RW, int GS) {
-    return align16((size_t)HP * RW * 4) + align16((size_t)HP * GS) + 32 * 5 * 4 + 32 * 4 + 5 * 32 + QRING;
-}
-
-__device__ inline WarpSmem carve(unsigned char *base, int HP, int RW, int GS) {
-    WarpSmem s;
-    s.obits = reinterpret_cast<uint32_t *>(base); base += align16((size_t)HP * RW * 4);
-    s.grid = base; base += align16((size_t)HP * GS);
-    s.tv = reinterpret_cast<float *>(base); base += 32 * 5 * 4;
-    s.mmask = reinterpret_cast<uint32_t *>(base); base += 32 * 4;
-    s.act = reinterpret_cast<int8_t *>(base); base += 32;
-    s.cls = reinterpret_cast<int8_t *>(base); base += 32;
-    s.st = reinterpret_cast<int8_t *>(base); base += 32;
-    s.commit = reinterpret_cast<int8_t *>(base); base += 32;
-    s.rep = reinterpret_cast<int8_t *>(base); base += 32;
-    s.queue = reinterpret_cast<int8_t *>(base);
-    return s;
-}
-
-constexpr int SOBW = 5;   // obstacle-bit words prefetched per lane (HP*RW <= 160: 40x40 with F = 9 needs 144)
-
-// inputs of one world, prefetched one world ahead of the one being resolved
-struct StepRegs {
-    uint32_t pw, gw;          // cell, goal of agent `lane`
-    int rep, act;             // repetition action, joint action
-    int st_in;                // MODE_JOINT: status computed earlier by mapf_evaluate
-    uint32_t ob[SOBW];        // obstacle bit words lane, lane+32, ...
-    int2 ht, ht2;             // human (pos,next) at the current tick and after this step's tick
-    int tick, hlen;
-};
-
-template <int MODE>
-__device__ __forceinline__ void load_step_world(const EnvView &v, const int8_t *__restrict__ actions,
-                                                const int8_t *__restrict__ status_in, int w, int lane, int nob,
-                                                uint64_t pol, StepRegs &r) {
-    if (w < v.W) {
-        const size_t idx = (size_t)w * v.N + (lane < v.N ? lane : 0);
-        r.pw = ld_keep(reinterpret_cast<const uint32_t *>(v.pos) + idx, pol);
-        r.gw = ld_keep(reinterpret_cast<const uint32_t *>(v.goal) + idx, pol);
-        r.rep = ld_keep_s8(v.rep + idx, pol);
-        r.act = __ldg(actions + idx);
-        r.st_in = (MODE == MODE_JOINT) ? (int)__ldg(status_in + idx) : 0;
-        const uint32_t *src = v.obst_bits + (size_t)w * nob;
-#pragma unroll
-        for (int k = 0; k < SOBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? ld_keep(src + k * 32 + lane, pol) : 0u;
-        r.ht = ld_keep_v2(reinterpret_cast<const int2 *>(v.hcur) + w, pol);
-        r.ht2 = ld_keep_v2(reinterpret_cast<const int2 *>(v.hnx) + w, pol);
-        r.tick = (int)ld_keep(v.htick + w, pol);
-        r.hlen = __ldg(v.hlen + w);
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOut &out, const WarpSmem &s, const int w,
-                                              const int lane, const StepRegs &in, const uint64_t pol) {
-    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW;
-    const bool active = lane < N;
-    const size_t idx = (size_t)w * N + (active ? lane : 0);
-    const uint32_t pw = in.pw, gw = in.gw;
-    const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
-    int goal_r = (int16_t)(gw & 0xffff), goal_c = (int16_t)(gw >> 16);
-    const int rep = in.rep;
-    int a = in.act;
-    uint32_t errbits = 0;
-    if (a < 0 || a >= NA) { if (active) errbits |= MAPF_ERR_BAD_ACTION; a = 0; }
-    const int tick = in.tick;
-    const int2 ht = in.ht;
-    const int hr = (int16_t)(ht.x & 0xffff), hc = (int16_t)((uint32_t)ht.x >> 16);
-    const int nr = (int16_t)(ht.y & 0xffff), nc = (int16_t)((uint32_t)ht.y >> 16);
-    __syncwarp();
-    const int gr = r + P, gc = c + P;
-    if (active) {
-        s.grid[gr * GS + gc] = (uint8_t)(lane + 1);
-        s.act[lane] = (int8_t)a;
-        s.rep[lane] = (int8_t)rep;
-    }
-    __syncwarp();
-
-    // ---- masks (getInvalidActions :339-360, getRestrictedActions :363-402, good :404-430) -------------------
-    uint32_t inv0 = 0, inv1 = 0;
-#pragma unroll
-    for (int k = 1; k < NA; ++k) {
-        const int tr = r + ((k == 2) - (k == 4)), tc = c + ((k == 1) - (k == 3));
-        if (row_bit(s.obits + (tr + P) * RW, tc + P)) inv0 |= 1u << k;                         // OOB or wall
-    }
-#pragma unroll
-    for (int k = 0; k < NA; ++k) {
-        const int tr = r + ((k == 2) - (k == 4)), tc = c + ((k == 1) - (k == 3));
-        const bool hv = (tr == nr && tc == nc) || (r == nr && c == nc && tr == hr && tc == hc);
-        if (hv && !(inv0 >> k & 1)) inv1 |= 1u << k;
-    }
-    uint32_t restr, confl, mmask;
-    scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.act, a, restr, confl, mmask);
-    const uint32_t repbit = rep >= 0 ? (1u << rep) : 0u;
-    const uint32_t good = ~(inv0 | inv1 | restr | repbit) & 31u;
-    const uint32_t abit = 1u << a;
-    const int tgt_r = r + dr_of(a), tgt_c = c + dc_of(a);
-
-    // ---- status (getActionStatus :434-480) -----------------------------------------------------------------
-    int st;
-    if (MODE == MODE_JOINT) {
-        st = in.st_in;
-    } else {
-        const int cls = (inv0 & abit) ? C_INV0 : (inv1 & abit) ? C_INV1 : (good & abit) ? C_GOOD : C_E;
-        st = cls == C_INV0 ? ST_STATIC : cls == C_INV1 ? ST_HUMAN : cls == C_GOOD ? ST_OK
-             : (confl & abit) ? ST_AGENT : (a == rep ? ST_REPEAT : ST_OK);
-        if (active) s.cls[lane] = (int8_t)cls;
-        __syncwarp();
-        bool trig = false;
-        if (active && cls == C_E) {
-            uint32_t m = mmask;
-            while (m) { const int j = __ffs(m) - 1; m &= m - 1; trig |= (s.cls[j] == C_INV1); }
-        }
-        if (__any_sync(FULL, trig)) {                       // rare: replay the sequential loop
-            if (active) { s.mmask[lane] = mmask; s.st[lane] = 0; }
-            __syncwarp();
-            if (lane == 0) {
-                for (int i = 0; i < N; ++i) {
-                    if (s.st[i] != 0) continue;
-                    const int ci = s.cls[i];
-                    if (ci == C_INV0) s.st[i] = ST_STATIC;
-                    else if (ci == C_INV1) s.st[i] = ST_HUMAN;
-                    else if (ci == C_GOOD) s.st[i] = ST_OK;
-                    else {
-                        uint32_t m = s.mmask[i];
-                        while (m) { const int j = __ffs(m) - 1; m &= m - 1; s.st[i] = ST_AGENT; s.st[j] = ST_AGENT; }
-                        if (s.st[i] == 0) s.st[i] = (s.act[i] == s.rep[i]) ? ST_REPEAT : ST_OK;
-                    }
-                }
-            }
-            __syncwarp();
-            if (active) st = s.st[lane];
-        }
-    }
-
-    // ---- reward / cost / trainValid (:483-550) -------------------------------------------------------------
-    float reward = st == ST_REPEAT ? -0.35f : st == ST_OK ? -0.3f : -2.0f;       // alg_parameters.py:36-43
-    const bool sg = active && st == ST_OK && tgt_r == goal_r && tgt_c == goal_c;       // shadowGoal :501-504
-    const uint32_t sgm = __ballot_sync(FULL, sg);
-    if (MODE != MODE_JOINT) {
-        if (active) {
-            if (out.status) out.status[idx] = (int8_t)st;
-            if (out.cost) {
-                const int d2 = (nr - tgt_r) * (nr - tgt_r) + (nc - tgt_c) * (nc - tgt_c);
-                // max(PENALTY_RADIUS - ||H' - T||, 0) / PENALTY_RADIUS in f64, then cast (:513-533)
-                out.cost[idx] = d2 < 25 ? (float)((5.0 - sqrt((double)d2)) / 5.0) : 0.0f;
-            }
-            if (MODE == MODE_EVALUATE && out.reward) out.reward[idx] = reward;
-        }
-        if (lane == 0 && out.shadow_goals) out.shadow_goals[w] = __popc(sgm);
-        if (out.train_valid) {
-            if (active) {
-#pragma unroll
-                for (int k = 0; k < NA; ++k) {
-                    const uint32_t b = 1u << k;
-                    s.tv[lane * NA + k] = (good & b) ? 1.0f : (restr & b) ? ((confl & b) ? 0.0f : 1.0f) : 0.0f;
-                }
-            }
-            __syncwarp();
-            float *dst = out.train_valid + (size_t)w * N * NA;
-            for (int k = lane; k < N * NA; k += 32) dst[k] = s.tv[k];
-        }
-        if (MODE == MODE_EVALUATE) {
-            const uint32_t eb = __reduce_or_sync(FULL, errbits);
-            if (lane == 0 && eb) atomicOr(v.err + w, eb);
-            __syncwarp();
-            if (active) s.grid[gr * GS + gc] = 0;
-            return;
-        }
-    }
-
-    // ---- fixActions (:552-612), only if some status is -1/-2/-3 (:617) ------------------------------------
-    int f = a;
-    const bool bad = active && (st == ST_STATIC || st == ST_HUMAN || st == ST_AGENT);
-    if (__any_sync(FULL, bad)) {
-        int commit = (st == ST_OK) ? a : -1;
-        const bool problem = active && st < 0;
-        if (problem && good) commit = __ffs(good) - 1;                         // goodActions[0] (:568-571)
-        if (active) s.commit[lane] = (int8_t)commit;
-        const bool inq = problem && !good;
-        const uint32_t qm = __ballot_sync(FULL, inq);
-        if (qm) {
-            if (inq) s.queue[__popc(qm & ((1u << lane) - 1u))] = (int8_t)lane;
-            int head = 0, tail = __popc(qm), iters = 0;
-            uint32_t draw = 0;
-            __syncwarp();
-            while (head < tail) {
-                if (++iters > FIX_CAP) { errbits |= MAPF_ERR_FIX_ITER_CAP; break; }
-                const int k = s.queue[(head++) & (QRING - 1)];
-                int new_tail = tail;
-                if (lane == k) {
-                    const uint32_t viable = ~(inv0 | inv1) & 31u;                 // :575
-                    uint32_t r2, c2, m2;
-                    scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, -1, r2, c2, m2);
-                    const uint32_t ok = viable & ~(restr & c2);                   // :577-584
-                    int choice;
-                    if (good) {
-                        choice = __ffs(good) - 1;                                 // an evicted agent may own a good action (:568)
-                    } else if (ok) {
-                        choice = __ffs(ok) - 1;
-                    } else if (!viable) {
-                        errbits |= MAPF_ERR_NO_VIABLE;                            // reference: IndexError (:588)
-                        choice = 0;
-                    } else {
-                        const int nv = __popc(viable);
-                        uint32_t ev = 0;
-                        if (v.TL > 0) {                                           // recorded random.choice + eviction order
-                            const int8_t *tp = v.tape + (size_t)w * v.TL;
-                            int cur = v.tape_cur[w];
-                            const int tl = v.tape_len[w];
-                            if (cur + 2 > tl) { errbits |= MAPF_ERR_TAPE; choice = __ffs(viable) - 1; cur = tl; }
-                            else {
-                                choice = tp[cur];
-                                const int ne = tp[cur + 1];
-                                if (choice < 0 || choice >= NA) { errbits |= MAPF_ERR_TAPE; choice = __ffs(viable) - 1; }
-                                scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
-                                uint32_t seen = 0;
-                                for (int q = 0; q < ne && cur + 2 + q < tl; ++q) {
-                                    const int j = tp[cur + 2 + q];
-                                    if (j >= 0 && j < N && (ev >> j & 1)) {
-                                        seen |= 1u << j;
-                                        s.commit[j] = -1;
-                                        s.queue[(new_tail++) & (QRING - 1)] = (int8_t)j;
-                                    }
-                                }
-                                if (seen != ev || __popc(ev) != ne) errbits |= MAPF_ERR_TAPE;
-                                ev = 0;
-                                cur += 2 + ne;
-                            }
-                            v.tape_cur[w] = cur;
-                        } else {                                                  // Philox stand-in, ascending eviction
-                            int pick = (int)(philox_draw(v.seed, (uint32_t)(w + v.world_offset), (uint32_t)v.nstep[w], draw) % (uint32_t)nv);
-                            uint32_t vm = viable;
-                            while (pick--) vm &= vm - 1;
-                            choice = __ffs(vm) - 1;
-                            scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
-                        }
-                        draw++;
-                        while (ev) {                                              // :593-596
-                            const int j = __ffs(ev) - 1; ev &= ev - 1;
-                            s.commit[j] = -1;
-                            s.queue[(new_tail++) & (QRING - 1)] = (int8_t)j;
-                        }
-                    }
-                    s.commit[lane] = (int8_t)choice;                              // :598
-                }
-                tail = __shfl_sync(FULL, new_tail, k);
-                draw = __shfl_sync(FULL, draw, k);
-                __syncwarp();
-            }
-        }
-        __syncwarp();
-        if (active) { f = s.commit[lane]; if (f < 0) f = 0; }
-    }
-
-    // ---- moves, goal arrival, human tick, constraint violations (:620-633) ----------------------------------
-    const int nr_ = r + dr_of(f), nc_ = c + dc_of(f);
-    const bool arrived = active && nr_ == goal_r && nc_ == goal_c;
-    const int t2 = (tick + 1 >= in.hlen) ? 0 : tick + 1;
-    const int2 ht2 = in.ht2;
-    const int h2r = (int16_t)(ht2.x & 0xffff), h2c = (int16_t)((uint32_t)ht2.x >> 16);
-    const bool viol = active && ((h2r - nr_) * (h2r - nr_) + (h2c - nc_) * (h2c - nc_) <= 24);   // cost_norm >= 0.01
-    if (active) {
-        st_keep(reinterpret_cast<uint32_t *>(v.pos) + idx, (uint32_t)(uint16_t)nr_ | ((uint32_t)(uint16_t)nc_ << 16), pol);
-        st_keep_s8(v.rep + idx, opp_of(f), pol);                                 // takeStep :158-161
-        if (arrived) {                                                           // Sequence.getNext util.py:33-39
-            int k = v.qcur[idx];
-            if (k >= v.Q) k = v.Q - 1; else v.qcur[idx] = k + 1;
-            st_keep(reinterpret_cast<uint32_t *>(v.goal) + idx,
-                    reinterpret_cast<const uint32_t *>(v.goal_queue)[idx * v.Q + k], pol);
-        }
-        if (out.goals_reached) out.goals_reached[idx] = arrived;
-        if (out.violated) out.violated[idx] = viol;
-        if (out.fixed_actions) out.fixed_actions[idx] = (int8_t)f;
-        if (MODE == MODE_FUSED && out.reward) out.reward[idx] = arrived ? __fadd_rn(reward, 1.5f) : reward;  // runner.py:89-91
-    }
-    const uint32_t am = __ballot_sync(FULL, arrived), vm_ = __ballot_sync(FULL, viol);
-    const uint32_t c1 = __ballot_sync(FULL, active && st == ST_STATIC), c2b = __ballot_sync(FULL, active && st == ST_HUMAN),
-                   c3 = __ballot_sync(FULL, active && st == ST_AGENT);
-    const uint32_t eb = __reduce_or_sync(FULL, errbits);
-    if (lane == 0) {
-        st_keep(v.htick + w, (uint32_t)t2, pol);
-        st_keep_v2(reinterpret_cast<int2 *>(v.hcur) + w, ht2, pol);
-        const int t3 = (t2 + 1 >= in.hlen) ? 0 : t2 + 1;          // keep the entry after next resident too
-        st_keep_v2(reinterpret_cast<int2 *>(v.hnx) + w, *reinterpret_cast<const int2 *>(v.htrace + ((size_t)w * v.L + t3) * 4), pol);
-        v.nstep[w] += 1;
-        if (eb) atomicOr(v.err + w, eb);
-        long long *cn = v.counters + (size_t)w * 6;                              // util.py:56-65, runner.py:66-99
-        cn[0] += __popc(am); cn[1] += __popc(sgm); cn[2] += __popc(c1); cn[3] += __popc(c2b); cn[4] += __popc(c3); cn[5] += __popc(vm_);
-    }
-    __syncwarp();
-    if (active) s.grid[gr * GS + gc] = 0;      // leave the id grid clean for the next world of this warp
-}
+using namespace sw;
 
 // Persistent CTAs, one warp per world at a time; worlds are claimed with one atomicAdd per warp and the next world's
 // inputs are loaded into registers while the current one is being resolved.
@@ -349,15 +41,16 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
         uint4 *g4 = reinterpret_cast<uint4 *>(s.grid);
         for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
     }
-    int w = claim_work(work_counter, 2, lane), w1 = w + 1;
+    int w = claim_work(work_counter, 1, lane);      // claim-then-load: see observe.cu
     const uint64_t pol = policy_evict_last();
+    const int pf_ahead = prefetch_ahead(v);
     StepRegs cur, nxt;
     load_step_world<MODE>(v, actions, status_in, w, lane, nob, pol, cur);
     const bool direct_ob = nob > SOBW * 32;
     while (w < v.W) {
-        int w2 = 0;
-        if (lane == 0) w2 = atomicAdd(work_counter, 1);
+        const int w1 = claim_work(work_counter, 1, lane);
         load_step_world<MODE>(v, actions, status_in, w1, lane, nob, pol, nxt);
+        if (lane == 0 && pf_ahead >= 0 && (w1 & (PFB - 1)) == 0) prefetch_world_batch(v, actions, w1 + pf_ahead, pol);
         if (!direct_ob) {
 #pragma unroll
             for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < nob) s.obits[k * 32 + lane] = cur.ob[k];
@@ -365,10 +58,10 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
             const uint32_t *src = v.obst_bits + (size_t)w * nob;
             for (int k = lane; k < nob; k += 32) s.obits[k] = __ldg(src + k);
         }
-        resolve_world<MODE>(v, out, s, w, lane, cur, pol);
+        uint32_t npw, ngw;
+        resolve_world<MODE>(v, out, s, w, lane, cur, pol, npw, ngw);
         __syncwarp();
         w = w1;
-        w1 = __shfl_sync(FULL, w2, 0);
         cur = nxt;
     }
     finish_work(work_counter, gridDim.x * (blockDim.x >> 5), lane);

@@ -173,19 +173,34 @@ class BatchedMapfGym:
         self._eval_key = None
         return o
 
+    def step_observe(self, actions, out: Optional[StepOut] = None, obs_out=None):
+        """One env step of the rollout loop in ONE launch: ``step(actions)`` then ``getAllObservations()`` of the new
+        state (runner.py:64-100), fused per world.  Returns ``(StepOut, obs, vec)``; bit-identical to the two calls."""
+        a = self._actions(actions)
+        o = self._out if out is None else out
+        obs, vec = self._obs_buffers(obs_out)
+        so = self._step_out(o)
+        _cabi.check(self._lib.mapf_step_observe(self._h, _ptr(a), C.byref(so), _ptr(obs), _ptr(vec), self._stream()),
+                    "mapf_step_observe")
+        self._eval_key = None
+        return o, obs, vec
+
     # ---- observations -----------------------------------------------------------------------------------------
-    def getAllObservations(self, out=None):
-        """``getAllObservations`` (mapf_gym.py:327-336).  ``out=(obs, vec)`` writes straight into the policy's input
-        tensors; otherwise env-owned tensors are (re)used."""
+    def _obs_buffers(self, out):
         if out is None:
             if self._obs is None:
                 self._obs = torch.empty((self.W, self.N, self.C, self.F, self.F), dtype=torch.float32, device=self.device)
                 self._vec = torch.empty((self.W, self.N, 4), dtype=torch.float32, device=self.device)
-            obs, vec = self._obs, self._vec
-        else:
-            obs, vec = out
-            assert obs.is_contiguous() and vec.is_contiguous() and obs.dtype == torch.float32 and vec.dtype == torch.float32
-            assert obs.numel() == self.W * self.N * self.C * self.F * self.F and vec.numel() == self.W * self.N * 4
+            return self._obs, self._vec
+        obs, vec = out
+        assert obs.is_contiguous() and vec.is_contiguous() and obs.dtype == torch.float32 and vec.dtype == torch.float32
+        assert obs.numel() == self.W * self.N * self.C * self.F * self.F and vec.numel() == self.W * self.N * 4
+        return obs, vec
+
+    def getAllObservations(self, out=None):
+        """``getAllObservations`` (mapf_gym.py:327-336).  ``out=(obs, vec)`` writes straight into the policy's input
+        tensors; otherwise env-owned tensors are (re)used."""
+        obs, vec = self._obs_buffers(out)
         _cabi.check(self._lib.mapf_observe(self._h, _ptr(obs), _ptr(vec), self._stream()), "mapf_observe")
         return obs, vec
 

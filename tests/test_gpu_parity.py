@@ -30,8 +30,9 @@ def _eq(a, b, msg):
     np.testing.assert_array_equal(a, b, err_msg=msg)
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("case", ENV_CASES)
-def test_gpu_matches_reference_trace(case):
+def test_gpu_matches_reference_trace(case, fused):
     g = Golden(case)
     env = _env(g.scenario)
     s = env.state()
@@ -42,7 +43,10 @@ def test_gpu_matches_reference_trace(case):
     _eq(_np(vec), g["vec"][0], "vec0")
     _eq(_np(env.bfs_maps()), g["bfs0"], "bfs0")
     for t in range(g.T):
-        out = env.step(torch.from_numpy(g["actions"][t]))
+        if fused:
+            out, obs, vec = env.step_observe(torch.from_numpy(g["actions"][t]))
+        else:
+            out = env.step(torch.from_numpy(g["actions"][t]))
         for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated"):
             _eq(_np(getattr(out, key)), g[key][t], f"{case} t={t} {key}")
         _eq(_np(out.shadow_goals), g["shadow"][t], f"{case} t={t} shadow")
@@ -51,7 +55,8 @@ def test_gpu_matches_reference_trace(case):
         assert not _np(s["err"]).any(), (case, t)
         _eq(_np(s["pos"]), g["pos"][t + 1], f"{case} t={t} pos")
         _eq(_np(s["goal"]), g["goal"][t + 1], f"{case} t={t} goal")
-        obs, vec = env.getAllObservations()
+        if not fused:
+            obs, vec = env.getAllObservations()
         _eq(_np(obs), g.obs[t + 1].astype(np.float32), f"{case} t={t} obs")
         _eq(_np(vec), g["vec"][t + 1], f"{case} t={t} vec")
     _eq(_np(env.bfs_maps()), g["bfsT"], "bfsT")
@@ -81,7 +86,7 @@ def test_gpu_five_call_api_matches_reference_trace(case):
         _eq(_np(env.state()["pos"]), g["pos"][t + 1], f"t={t} pos")
 
 
-def _run_vs_oracle(sc, T, seed=1234, check_obs_every=1, threads=8):
+def _run_vs_oracle(sc, T, seed=1234, check_obs_every=1, threads=8, fused=False):
     orc = OracleMapfGym(sc, seed=seed, threads=threads, use_tape=False)
     env = _env(sc, seed=seed, use_tape=False)
     acts = random_actions(T, sc.num_worlds, sc.num_agents, seed=seed)
@@ -90,7 +95,10 @@ def _run_vs_oracle(sc, T, seed=1234, check_obs_every=1, threads=8):
     assert torch.equal(obs, torch.from_numpy(o_obs).cuda()) and torch.equal(vec, torch.from_numpy(o_vec).cuda())
     for t in range(T):
         ref = orc.step(acts[t])
-        out = env.step(torch.from_numpy(acts[t]))
+        if fused:       # mapf_step_observe: one launch for the step and the observations of the new state
+            out, obs, vec = env.step_observe(torch.from_numpy(acts[t]))
+        else:
+            out = env.step(torch.from_numpy(acts[t]))
         ok_w = orc.state()["err"] == 0          # worlds where the reference would have raised are excluded
         e_gpu = _np(env.state()["err"]).astype(np.uint32)
         np.testing.assert_array_equal(e_gpu, orc.state()["err"], err_msg=f"t={t} err flags")
@@ -104,7 +112,8 @@ def _run_vs_oracle(sc, T, seed=1234, check_obs_every=1, threads=8):
         _eq(_np(s["rep"])[ok_w], so["rep"][ok_w], f"t={t} rep")
         if t % check_obs_every == 0 or t == T - 1:
             o_obs, o_vec = orc.getAllObservations(out=(o_obs, o_vec))
-            obs, vec = env.getAllObservations()
+            if not fused:
+                obs, vec = env.getAllObservations()
             okd = torch.from_numpy(ok_w).cuda()
             assert torch.equal(obs[okd], torch.from_numpy(o_obs).cuda()[okd]), f"t={t} obs"
             assert torch.equal(vec[okd], torch.from_numpy(o_vec).cuda()[okd]), f"t={t} vec"
@@ -123,6 +132,35 @@ def test_gpu_matches_oracle_config2_4096x20x20x8():
 def test_gpu_matches_oracle_config3_shape_40x40x32():
     sc = random_scenario(768, 40, 40, 32, density=(0.0, 0.3), queue_len=8, seed=12, unique_maps=96)
     _run_vs_oracle(sc, T=32, check_obs_every=4)
+
+
+@pytest.mark.parametrize("shape", [(1024, 40, 40, 32, 6), (512, 20, 20, 8, 6), (300, 8, 8, 8, 5), (64, 33, 65, 5, 6),
+                                   (40, 64, 64, 31, 6), (7, 7, 11, 1, 6)])
+def test_gpu_fused_step_observe_matches_oracle(shape):
+    """mapf_step_observe (the fused launch) against the oracle, every step, incl. crowded worlds and odd shapes."""
+    W, H, Wd, N, C = shape
+    dens = (0.2, 0.3) if H == 8 else (0.0, 0.3)
+    sc = random_scenario(W, H, Wd, N, density=dens, queue_len=4, seed=W + N, num_channel=C, unique_maps=min(W, 64))
+    _run_vs_oracle(sc, T=24, fused=True)
+
+
+def test_gpu_fused_step_observe_equals_two_calls_and_falls_back():
+    """Same bits from the fused launch and from step + getAllObservations; shapes the fused kernel does not cover
+    (N > 32, FOV 31 with 32 agents) go through the two kernels behind the same entry point."""
+    for (W, H, N, fov) in ((2048, 40, 32, 9), (16, 40, 32, 31), (12, 48, 48, 9), (64, 20, 8, 15)):
+        sc = random_scenario(W, H, H, N, density=(0.0, 0.3), queue_len=4, seed=fov + N, fov=fov, unique_maps=min(W, 32))
+        a = torch.from_numpy(random_actions(12, W, N, seed=4)).cuda()
+        e1, e2 = _env(sc, use_tape=False), _env(sc, use_tape=False)
+        for t in range(12):
+            o1 = e1.step(a[t]); obs1, vec1 = e1.getAllObservations()
+            o2, obs2, vec2 = e2.step_observe(a[t])
+            for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals",
+                        "fixed_actions"):
+                assert torch.equal(getattr(o1, key), getattr(o2, key)), (W, H, N, fov, t, key)
+            assert torch.equal(obs1, obs2) and torch.equal(vec1, vec2), (W, H, N, fov, t)
+        s1, s2 = e1.state(), e2.state()
+        assert all(torch.equal(s1[k], s2[k]) for k in s1)
+        assert torch.equal(e1.counters(), e2.counters())
 
 
 def test_gpu_matches_oracle_crowded_fixactions_philox():
