@@ -139,6 +139,13 @@ int mapf_bfs_refresh(MapfEnv *env, const uint8_t *goals_reached, int16_t *bfs_ma
 int mapf_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, double gamma,
              double lam, int32_t T, int64_t cols, float *returns, float *adv, void *stream);
 
+/* Joint-action sampling on device — replaces the per-agent host loop `np.random.choice(range(N_ACTIONS), p=ps[i])`
+ * of Model.step / Model.evaluate (model.py:38-40, 58-59).  ps: f32 [rows,5] probabilities (rows = W*N); actions: int8
+ * [rows]; chosen_p (optional): f32 [rows] probability of the drawn action.  Philox4x32-10 keyed by (seed; row, draw):
+ * call with draw = 0, 1, 2, ... for successive steps.  Same distribution as the reference, not the same bits. */
+int mapf_sample_actions(const float *ps, int64_t rows, uint64_t seed, uint32_t draw, int8_t *actions, float *chosen_p,
+                        void *stream);
+
 /* State read-back for checks and checkpoints (device pointers; any may be NULL):
  * pos/goal int16 [W,N,2], rep int8 [W,N] (the repetition action or -1, mapf_gym.py:161), err u32 [W]. */
 int mapf_get_state(MapfEnv *env, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream);

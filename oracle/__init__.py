@@ -3,4 +3,4 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
 import this package.  The product package ``primal_ppo_b200`` never imports it.
 """
-from .oracle import OracleMapfGym, build_oracle, gae_oracle, oracle_lib_path  # noqa: F401
+from .oracle import OracleMapfGym, build_oracle, gae_oracle, oracle_lib_path, sample_actions_oracle  # noqa: F401

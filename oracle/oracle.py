@@ -58,6 +58,7 @@ def _load():
         lib.orc_step_observe.argtypes = [p] * 12
         lib.orc_state.argtypes = [p, p, p, p, p, p]
         lib.orc_gae.argtypes = [p, p, p, C.c_double, C.c_double, C.c_int, C.c_int, p, p]
+        lib.orc_sample_actions.argtypes = [p, C.c_longlong, C.c_uint64, C.c_uint32, p, p]
         lib.orc_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -201,6 +202,17 @@ def gae_oracle(rewards, values, last_values, gamma=0.95, lam=0.95):
     adv = np.empty_like(r)
     lib.orc_gae(_ptr(r), _ptr(v), _ptr(lv), float(gamma), float(lam), T, cols, _ptr(ret), _ptr(adv))
     return ret, adv
+
+
+def sample_actions_oracle(ps, seed=1234, draw=0):
+    """model.py:38-40 with Philox draws (see orc_sample_actions). ps: f32 [..., 5] -> (int8 [...], f32 [...])."""
+    lib = _load()
+    p = np.ascontiguousarray(ps, dtype=np.float32)
+    rows = p.size // 5
+    a = np.empty(p.shape[:-1], dtype=np.int8)
+    cp = np.empty(p.shape[:-1], dtype=np.float32)
+    lib.orc_sample_actions(_ptr(p), rows, int(seed) & (2 ** 64 - 1), int(draw) & 0xffffffff, _ptr(a), _ptr(cp))
+    return a, cp
 
 
 def max_threads() -> int:

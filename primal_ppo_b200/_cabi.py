@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_PKG, "libmapf_b200.so")
 
 EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_reset", "mapf_evaluate",
             "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae",
-            "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe"]
+            "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe",
+            "mapf_sample_actions"]
 
 ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE = 1, 2, 4, 8
 
@@ -68,6 +69,7 @@ def load_library():
     lib.mapf_bfs.argtypes = [vp, vp, i64, vp, vp]
     lib.mapf_bfs_refresh.argtypes = [vp, vp, vp, vp]
     lib.mapf_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp, vp, vp]
+    lib.mapf_sample_actions.argtypes = [vp, i64, C.c_uint64, C.c_uint32, vp, vp, vp]
     lib.mapf_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.mapf_get_counters.argtypes = [vp, vp, vp]
     lib.mapf_step_observe_host.argtypes = [vp, vp, C.POINTER(MapfStepOutHost), vp, vp, vp, vp, vp, vp]

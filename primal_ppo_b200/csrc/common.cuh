@@ -184,6 +184,9 @@ cudaError_t launch_arrivals(const EnvView &v, const uint8_t *goals, int32_t *lis
 cudaError_t launch_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, float g, float gl,
                        int T, long long cols, float *ret, float *adv, cudaStream_t s);
 
+cudaError_t launch_sample_actions(const float *ps, long long rows, unsigned long long seed, uint32_t draw, int8_t *actions,
+                                  float *chosen_p, cudaStream_t s);
+
 constexpr int MODE_EVALUATE = 0, MODE_JOINT = 1, MODE_FUSED = 2;
 
 }  // namespace mapf

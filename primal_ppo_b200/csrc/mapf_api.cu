@@ -271,6 +271,14 @@ int mapf_gae(const float *r, const float *v, const float *last_v, const uint8_t 
     return MAPF_OK;
 }
 
+int mapf_sample_actions(const float *ps, int64_t rows, uint64_t seed, uint32_t draw, int8_t *actions, float *chosen_p,
+                        void *stream) {
+    if (!ps || !actions) return fail(MAPF_E_NULL, "mapf_sample_actions: null argument");
+    if (rows < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_sample_actions: rows < 0");
+    CU(launch_sample_actions(ps, rows, seed, draw, actions, chosen_p, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
 int mapf_get_state(MapfEnv *e, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream) {
     if (!e) return fail(MAPF_E_NULL, "mapf_get_state: null env");
     const size_t WN = (size_t)e->v.W * e->v.N;

@@ -301,3 +301,20 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, last_values: torch.Tensor, 
         _cabi.check(lib.mapf_gae(_ptr(r), _ptr(v), _ptr(lv), _ptr(nt), float(gamma), float(lam), T, cols, _ptr(ret),
                                  _ptr(adv), stream), "mapf_gae")
     return (ret, adv) if return_advantages else ret
+
+
+def sample_actions(ps: torch.Tensor, seed: int = 1234, draw: int = 0, out: Optional[torch.Tensor] = None,
+                   chosen_p: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Joint-action sampling on device (model.py:38-40): ps f32 [..., 5] -> int8 [...] actions."""
+    lib = _cabi.load_library()
+    assert ps.is_cuda and ps.dtype == torch.float32 and ps.shape[-1] == 5
+    p = ps.contiguous()
+    rows = p.numel() // 5
+    if out is None:
+        out = torch.empty(p.shape[:-1], dtype=torch.int8, device=p.device)
+    assert out.is_contiguous() and out.dtype == torch.int8 and out.numel() == rows
+    stream = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+    with torch.cuda.device(p.device):
+        _cabi.check(lib.mapf_sample_actions(_ptr(p), rows, int(seed) & (2 ** 64 - 1), int(draw) & 0xffffffff, _ptr(out),
+                                            _ptr(chosen_p), stream), "mapf_sample_actions")
+    return out
