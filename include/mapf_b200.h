@@ -154,6 +154,36 @@ int mapf_get_state(MapfEnv *env, int16_t *pos, int16_t *goal, int8_t *rep, uint3
  * int64 [W,6] = totalGoals, shadowGoals, staticCollide, humanCollide, agentCollide, constraintViolations. */
 int mapf_get_counters(MapfEnv *env, int64_t *counters, void *stream);
 
+/* ---- on-device scenario generation (throughput mode) ------------------------------------------------------------ */
+
+/* Replaces, for W worlds at once, what MapfGym.__init__ draws on the host: the map (generateWarehouse,
+ * map_generator.py:127-138, or the PRIMAL density map, map_generator.py:13-28), the human's entrance / goal / walk
+ * (mapf_gym.py:9-50, astar_4.py) and the agents' starts and goals (populateMap mapf_gym.py:175-190, getFreeCell
+ * util.py:67-76).  Philox4x32-10 keyed by (seed; world_offset + w, stream, draw): equal to the reference in distribution,
+ * not in bits; the warehouse layout for a drawn length is bit-identical to generateWarehouse. */
+typedef struct MapfGenConfig {
+    int32_t num_worlds, height, width, num_agents; /* array shapes: every world is stored as height x width */
+    int32_t kind;          /* 0 = density map, 1 = warehouse */
+    int32_t density_mode;  /* kind 0: 0 = p ~ U[lo, hi], 1 = np.random.triangular(lo, .33 lo + .66 hi, hi) (map_generator.py:18) */
+    float density_lo, density_hi;
+    int32_t size_lo, size_hi; /* kind 1: length ~ U{lo..hi}, cols = int(length * 1.5); kind 0: side from {lo, (lo+hi)/2, hi}
+                                 w.p. (.5, .25, .25) (map_generator.py:19), or fixed height x width when size_lo <= 0 */
+    int32_t queue_len;     /* Q goals per agent */
+    int32_t trace_len;     /* L ticks of human trace per world */
+    int32_t human_loops;   /* 1 = LoopingHuman (one out-and-back walk, repeated); k > 1 = up to k walks with re-drawn goals
+                              (Human.getNextGoal, mapf_gym.py:41-43) before the trace wraps */
+    uint64_t seed;
+    int32_t world_offset;  /* global index of world 0 (sharded jobs) */
+    int32_t device;
+} MapfGenConfig;
+
+/* gen_err bits (per world, optional): 1 too few free cells, 2 no free cell on row 0 / column 0 (the reference would spin
+ * forever in getEntrance), 4 no reachable goal within trace_len (human stands still), 8 an agent could not be placed. */
+int mapf_generate_scenario(const MapfGenConfig *cfg, uint8_t *obst /*[W,H,Wd]*/, int16_t *dims /*[W,2]*/,
+                           int16_t *starts /*[W,N,2]*/, int16_t *goal_queue /*[W,N,Q,2]*/, int16_t *htrace /*[W,L,4]*/,
+                           int32_t *hlen /*[W]*/, int16_t *hp5 /*[W,5,2] or NULL*/, uint32_t *gen_err /*[W] or NULL*/,
+                           void *stream);
+
 /* ---- host-buffer entry points (what a CPU-side runner calls; copies are inside the call) ---------------- */
 
 /* Host mirror of MapfStepOut: PINNED or pageable host memory; any pointer may be NULL. */

@@ -6,7 +6,7 @@ sm_100a CUDA kernels behind the C ABI of ``include/mapf_b200.h`` (``libmapf_b200
 from .scenario import Scenario, random_scenario, random_actions, looping_trace  # noqa: F401
 
 __all__ = ["Scenario", "random_scenario", "random_actions", "looping_trace", "BatchedMapfGym", "StepOut", "gae",
-           "sample_actions"]
+           "sample_actions", "DeviceScenario", "generate_scenario_device"]
 
 
 def __getattr__(name):
@@ -14,4 +14,7 @@ def __getattr__(name):
     if name in ("BatchedMapfGym", "StepOut", "gae", "sample_actions"):
         from . import vec_env
         return getattr(vec_env, name)
+    if name in ("DeviceScenario", "generate_scenario_device"):
+        from . import device_scenario
+        return getattr(device_scenario, name)
     raise AttributeError(name)

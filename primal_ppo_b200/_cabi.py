@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libmapf_b200.so")
 EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_reset", "mapf_evaluate",
             "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae",
             "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe",
-            "mapf_sample_actions"]
+            "mapf_sample_actions", "mapf_generate_scenario"]
 
 ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE = 1, 2, 4, 8
 
@@ -23,6 +23,13 @@ class MapfConfig(C.Structure):
                 ("fov", C.c_int32), ("num_channel", C.c_int32), ("use_da", C.c_int32), ("use_hp", C.c_int32),
                 ("queue_len", C.c_int32), ("trace_len", C.c_int32), ("tape_stride", C.c_int32),
                 ("hp5_per_tick", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("world_offset", C.c_int32)]
+
+
+class MapfGenConfig(C.Structure):
+    _fields_ = [("num_worlds", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("num_agents", C.c_int32),
+                ("kind", C.c_int32), ("density_mode", C.c_int32), ("density_lo", C.c_float), ("density_hi", C.c_float),
+                ("size_lo", C.c_int32), ("size_hi", C.c_int32), ("queue_len", C.c_int32), ("trace_len", C.c_int32),
+                ("human_loops", C.c_int32), ("seed", C.c_uint64), ("world_offset", C.c_int32), ("device", C.c_int32)]
 
 
 class MapfScenario(C.Structure):
@@ -70,6 +77,7 @@ def load_library():
     lib.mapf_bfs_refresh.argtypes = [vp, vp, vp, vp]
     lib.mapf_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp, vp, vp]
     lib.mapf_sample_actions.argtypes = [vp, i64, C.c_uint64, C.c_uint32, vp, vp, vp]
+    lib.mapf_generate_scenario.argtypes = [C.POINTER(MapfGenConfig)] + [vp] * 9
     lib.mapf_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.mapf_get_counters.argtypes = [vp, vp, vp]
     lib.mapf_step_observe_host.argtypes = [vp, vp, C.POINTER(MapfStepOutHost), vp, vp, vp, vp, vp, vp]

@@ -187,6 +187,9 @@ cudaError_t launch_gae(const float *r, const float *v, const float *last_v, cons
 cudaError_t launch_sample_actions(const float *ps, long long rows, unsigned long long seed, uint32_t draw, int8_t *actions,
                                   float *chosen_p, cudaStream_t s);
 
+cudaError_t launch_scenario_gen(const MapfGenConfig &c, uint8_t *obst, int16_t *dims, int16_t *starts, int16_t *goal_queue,
+                                int16_t *htrace, int32_t *hlen, int16_t *hp5, uint32_t *gen_err, cudaStream_t s);
+
 constexpr int MODE_EVALUATE = 0, MODE_JOINT = 1, MODE_FUSED = 2;
 
 }  // namespace mapf

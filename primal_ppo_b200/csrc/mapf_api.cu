@@ -279,6 +279,29 @@ int mapf_sample_actions(const float *ps, int64_t rows, uint64_t seed, uint32_t d
     return MAPF_OK;
 }
 
+int mapf_generate_scenario(const MapfGenConfig *c, uint8_t *obst, int16_t *dims, int16_t *starts, int16_t *goal_queue,
+                           int16_t *htrace, int32_t *hlen, int16_t *hp5, uint32_t *gen_err, void *stream) {
+    if (!c || !obst || !dims || !starts || !goal_queue || !htrace || !hlen)
+        return fail(MAPF_E_NULL, "mapf_generate_scenario: null argument");
+    if (c->num_worlds < 1 || c->height < 2 || c->width < 2 || c->num_agents < 1 || c->queue_len < 1 || c->trace_len < 1)
+        return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: bad sizes");
+    if (c->height > 128 || c->width > 128) return fail(MAPF_E_UNSUPPORTED, "mapf_generate_scenario: H, Wd <= 128 supported");
+    if (c->kind == 1) {
+        if (c->size_lo < 4 || c->size_hi < c->size_lo) return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: warehouse needs 4 <= size_lo <= size_hi");
+        if (c->size_hi > c->height || (int)((double)c->size_hi / (2.0 / 3.0)) > c->width)
+            return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: warehouse of length %d needs height >= %d and width >= %d",
+                        c->size_hi, c->size_hi, (int)((double)c->size_hi / (2.0 / 3.0)));
+    } else if (c->kind == 0) {
+        if (c->density_lo < 0.f || c->density_hi < c->density_lo || c->density_hi >= 1.f)
+            return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: need 0 <= density_lo <= density_hi < 1");
+        if (c->size_lo > 0 && (c->size_hi < c->size_lo || c->size_hi > c->height || c->size_hi > c->width))
+            return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: size range does not fit height x width");
+    } else return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: kind must be 0 (density) or 1 (warehouse)");
+    CU(cudaSetDevice(c->device));
+    CU(launch_scenario_gen(*c, obst, dims, starts, goal_queue, htrace, hlen, hp5, gen_err, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
 int mapf_get_state(MapfEnv *e, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream) {
     if (!e) return fail(MAPF_E_NULL, "mapf_get_state: null env");
     const size_t WN = (size_t)e->v.W * e->v.N;

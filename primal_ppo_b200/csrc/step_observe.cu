@@ -27,7 +27,7 @@ step_observe_kernel(const EnvView v, const int8_t *__restrict__ actions, const M
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint4 lut[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int HP = v.HP, RW = v.RW, GS = v.GS, nob = v.HP * v.RW;
+    const int HP = v.HP, GS = v.GS, nob = v.HP * v.RW;
     unsigned char *base = smem_raw + (size_t)warp * per_warp;
     const ObsSmem m = obs_carve(base, L, v.N);
     // the step phase shares the obstacle bit rows and the agent-id grid with the observe phase; its own scratch

@@ -48,7 +48,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class BatchedMapfGym:
-    def __init__(self, scenario: Scenario, device=None, seed: int = 1234, use_tape: bool = True,
+    def __init__(self, scenario, device=None, seed: int = 1234, use_tape: bool = True,
                  world_offset: int = 0):
         if not torch.cuda.is_available():
             raise _cabi.MapfError("BatchedMapfGym needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -61,8 +61,12 @@ class BatchedMapfGym:
         self.num_channel, self.use_da, self.use_hp = sc.num_channel, sc.use_da, sc.use_hp
         tape = sc.tape if (use_tape and sc.tape is not None) else None
 
-        def up(a):
-            return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        def up(a):      # numpy arrays are uploaded; tensors of a DeviceScenario are used in place
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                return a.to(self.device).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
         # scenario arrays are borrowed by the C side: keep them alive here
         self._sc = dict(obst=up(sc.obst), starts=up(sc.starts), goal_queue=up(sc.goal_queue), htrace=up(sc.htrace),
                         hlen=up(sc.hlen), hp5=up(sc.hp5), tape=up(tape),
