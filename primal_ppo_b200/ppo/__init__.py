@@ -5,3 +5,4 @@ from .lagrange import Lagrangian, PIDLagrangian, make_lagrangian  # noqa: F401
 from .loss import PPOConfig, normalize_advantages, ppo_lagrange_loss  # noqa: F401
 from .policy import REFERENCE_KEY_MAP, ScrimpPolicy  # noqa: F401
 from .trainer import RolloutBuffer, VecPPOTrainer  # noqa: F401
+from .evaluate import evaluate_fixed_episodes  # noqa: F401,E402

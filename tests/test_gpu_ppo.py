@@ -95,3 +95,23 @@ def test_gpu_policy_bf16_autocast_close_to_fp32():
             lo = pol(obs, vec)
     assert float((ref.policy - lo.policy.float()).abs().max()) < 3e-2
     assert float((ref.value - lo.value.float()).abs().max()) < 0.15
+
+
+def test_gpu_evaluate_fixed_episodes_from_reference_fixture():
+    """evaluate.py's loop, batched: the reference's fixture folder -> Scenario -> all episodes at once."""
+    import os
+    from primal_ppo_b200.episode_io import load_fixed_episode_infos, scenario_from_fixed_episode_infos
+    from primal_ppo_b200.ppo import ScrimpPolicy, evaluate_fixed_episodes
+    fix = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixed_episode_infos")
+    sc = scenario_from_fixed_episode_infos(load_fixed_episode_infos(fix), max_steps=48, use_da=True, use_hp=True)
+    torch.manual_seed(0)
+    pol = ScrimpPolicy().cuda().eval()
+    res = evaluate_fixed_episodes(pol, sc, max_steps=48, greedy=False, model_name="PPOL-HP+DA", frames_for_world=1)
+    per, m = res["per_episode"], res["metrics"]
+    assert per["episodeReward"].shape == (4,) and (per["episodeReward"] < 0).all() and not per["err"].any()
+    assert set(k.split("/")[1] for k in m) == {f"{a}_per_agent{b}" for a in ("hc", "cv", "ecr", "goals") for b in ("", "_per_timestep")}
+    assert abs(m["PPOL-HP+DA/goals_per_agent/mean"] - per["totalGoals"].mean() / 3) < 1e-12
+    assert len(res["frames"]) == 49 and res["frames"][0].dtype == np.uint8
+    res2 = evaluate_fixed_episodes(pol, sc, max_steps=48, greedy=True)
+    res3 = evaluate_fixed_episodes(pol, sc, max_steps=48, greedy=True)
+    assert np.array_equal(res2["per_episode"]["episodeReward"], res3["per_episode"]["episodeReward"])   # greedy is deterministic
