@@ -8,7 +8,7 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libmapf_b200.so")
-SOURCES = ["mapf_api.cu", "step.cu", "step_wide.cu", "observe.cu", "step_observe.cu", "bfs.cu", "gae.cu", "glue.cu", "scenario_gen.cu"]
+SOURCES = ["mapf_api.cu", "step.cu", "step_wide.cu", "observe.cu", "observe_wide.cu", "step_observe.cu", "bfs.cu", "gae.cu", "glue.cu", "scenario_gen.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC,-fvisibility=default", "-shared", "-cudart", "shared"]
 

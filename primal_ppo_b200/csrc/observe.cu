@@ -101,6 +101,11 @@ cudaError_t launch_t(const EnvView &v, float *obs, float *vec, const ObsLayout &
 
 cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t stream) {
     const int PB = v.C * v.F * v.F;
+    // worlds whose block needs several warp passes: one CTA per world with shared staging (observe_wide.cu)
+    if ((v.N > 32 || (size_t)v.N * ((PB + 31) / 32 + 2) * 4 * 2 > 24 * 1024 || (v.dbg_flags & 4)) && !(v.dbg_flags & 2)) {
+        const cudaError_t e = launch_observe_wide(v, obs, vec, work_counter, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     // chunk of agents handled per phase-1 pass: as many as fit ~24 KB of bit-string scratch per warp
     int CH = v.N < 32 ? v.N : 32;
     while (CH > 4 && (size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 24 * 1024) CH >>= 1;

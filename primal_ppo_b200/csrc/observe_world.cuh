@@ -92,6 +92,151 @@ __device__ __forceinline__ ObsSmem obs_carve(unsigned char *base, const ObsLayou
     return m;
 }
 
+// One chunk of agents [c0, c0 + nch) of a staged world by one warp: phase 1 (per-agent bit strings), phase 1b
+// (compaction), phase 2 (bits -> f32, streaming stores).  `aw` / `wb` are this warp's scratch; everything else of `m` is
+// read-only here and may be shared by the warps of a CTA.
+template <int C_T, int F_T, bool VEC4>
+__device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout &L, const ObsSmem &m, const uint4 *lut,
+                                              const int w, const int lane, const int c0, const int nch, const int nr,
+                                              const int nc, const int rows, const int cols, float *__restrict__ obs,
+                                              float *__restrict__ vec) {
+    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW;
+    const int F = F_T > 0 ? F_T : v.F, C = C_T > 0 ? C_T : v.C, half = F >> 1;
+    const int FF = F * F, PB = (C_T > 0 && F_T > 0) ? C_T * F_T * F_T : L.PB, AST = L.AST;
+    const uint32_t *const obits = m.obits, *const abits = m.abits, *const sgoal = m.sgoal, *const spos = m.spos;
+    uint32_t *const aw = m.aw, *const wb = m.wb;
+    const uint8_t *const grid = m.grid;
+    {
+        const int i = c0 + lane;
+        const bool act = lane < nch;
+        // ---- phase 1: per-agent bit strings -------------------------------------------------------------------
+        if (act) {
+            uint32_t *my = aw + lane * AST;
+            const uint32_t pw = spos[i], gw = sgoal[i];
+            const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
+            const int gr = (int16_t)(gw & 0xffff), gc = (int16_t)(gw >> 16);
+            const int top = r - half, left = c - half;                                    // :251
+            const int off = left + P;
+            if (F_T > 0) {
+                // channels 0 and 1 accumulate in registers at compile-time bit positions
+                constexpr int FT = F_T > 0 ? F_T : 1;
+                constexpr int NACC = (2 * FT * FT + 31) / 32 + 1;
+                uint32_t acc[NACC];
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) acc[k] = 0;
+#pragma unroll
+                for (int y = 0; y < FT; ++y) {
+                    const int prow = top + y + P;
+                    uint32_t o = row_window(obits + prow * RW, off, FT);      // OOB or obstacle  (:270-276)
+                    uint32_t g = row_window(abits + prow * RW, off, FT);      // agents           (:278-285)
+                    if (y == FT / 2) { o |= 1u << (FT / 2); g &= ~(1u << (FT / 2)); }   // own cell -> channel 0 (:278-280)
+                    constexpr int dummy = 0; (void)dummy;
+                    const int p0 = y * FT, p1 = FT * FT + y * FT;
+                    acc[p0 >> 5] |= o << (p0 & 31);
+                    if ((p0 & 31) + FT > 32) acc[(p0 >> 5) + 1] |= o >> (32 - (p0 & 31));
+                    acc[p1 >> 5] |= g << (p1 & 31);
+                    if ((p1 & 31) + FT > 32) acc[(p1 >> 5) + 1] |= g >> (32 - (p1 & 31));
+                }
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) my[k] = acc[k];
+                for (int k = NACC; k < AST; ++k) my[k] = 0;
+            } else {
+                for (int k = 0; k < AST; ++k) my[k] = 0;
+                for (int y = 0; y < F; ++y) {
+                    const int prow = top + y + P;
+                    uint32_t o = row_window(obits + prow * RW, off, F);
+                    uint32_t g = row_window(abits + prow * RW, off, F);
+                    if (y == half) { o |= 1u << half; g &= ~(1u << half); }
+                    or_bits(my, y * F, o, F);
+                    or_bits(my, FF + y * F, g, F);
+                }
+            }
+            // channel 3: goals of the agents visible in the window, clamped into it (:302-308)
+            for (int y = 0; y < F; ++y) {
+                const int prow = top + y + P;
+                uint32_t g = row_window(abits + prow * RW, off, F);
+                if (y == half) g &= ~(1u << half);
+                while (g) {
+                    const int x = __ffs(g) - 1; g &= g - 1;
+                    const int j = grid[prow * GS + off + x] - 1;
+                    const uint32_t jw = sgoal[j];
+                    const int jr = (int16_t)(jw & 0xffff), jc = (int16_t)(jw >> 16);
+                    const int mr = max(top, min(top + F - 1, jr)), mc = max(left, min(left + F - 1, jc));
+                    or_bit(my, 3 * FF + (mr - top) * F + (mc - left));
+                }
+            }
+            if (v.use_da) {                                              // danger disc |cell - H'| <= 5 (:289-290)
+                for (int y = 0; y < F; ++y) {
+                    const int rr = top + y, dy = rr > nr ? rr - nr : nr - rr;
+                    if (rr >= 0 && rr < rows && dy <= 5) {
+                        const int hw = dy == 0 ? 5 : dy <= 3 ? 4 : dy == 4 ? 3 : 0;
+                        const int lo = max(max(nc - hw, 0), left), hi = min(min(nc + hw, cols - 1), left + F - 1);
+                        if (lo <= hi) or_bits(my, 4 * FF + y * F + (lo - left), (1u << (hi - lo + 1)) - 1u, hi - lo + 1);
+                    }
+                }
+            }
+            if (gr >= top && gr < top + F && gc >= left && gc < left + F)                  // own goal (:298-300)
+                or_bit(my, 2 * FF + (gr - top) * F + (gc - left));
+            if (nr >= top && nr < top + F && nc >= left && nc < left + F)                  // human (:310-312)
+                or_bit(my, 4 * FF + (nr - top) * F + (nc - left));
+            if (v.use_hp && C == 6 && v.hp5) {                                             // (:293-297)
+                const int tick = v.htick[w];
+                const int16_t *p5 = v.hp5 + (v.hp5_per_tick ? ((size_t)w * v.L + tick) * 10 : (size_t)w * 10);
+                for (int k = 0; k < 5; ++k) {
+                    const int pr = p5[2 * k], pc = p5[2 * k + 1];
+                    if (pr >= 0 && pr < rows && pc >= 0 && pc < cols && pr >= top && pr < top + F && pc >= left && pc < left + F)
+                        or_bit(my, 5 * FF + (pr - top) * F + (pc - left));
+                }
+            }
+            // vector (:316-323): f64 sqrt / divide, then cast
+            const double dx = (double)(gr - r), dy_ = (double)(gc - c);
+            const double d = sqrt(dx * dx + dy_ * dy_);
+            float4 o4;
+            o4.x = (float)(d != 0.0 ? dx / d : dx);
+            o4.y = (float)(d != 0.0 ? dy_ / d : dy_);
+            o4.z = (float)d;
+            o4.w = 0.0f;
+            reinterpret_cast<float4 *>(vec)[(size_t)w * N + i] = o4;
+        }
+        __syncwarp();
+        // ---- phase 1b: compact to one contiguous bit string (word m <- 32 bits starting at agent n, bit e) --------
+        const int TB = nch * PB;
+        const int nwords = (TB + 31) >> 5;
+        {
+            int n = (lane << 5) / PB, e = (lane << 5) - n * PB;
+            for (int m = lane; m < nwords; m += 32) {
+                const uint32_t *src = aw + n * AST;
+                uint32_t x = __funnelshift_r(src[e >> 5], src[(e >> 5) + 1], e & 31);
+                const int valid = PB - e;
+                if (valid < 32) {
+                    x &= (1u << valid) - 1u;
+                    if (n + 1 < nch) x |= aw[(n + 1) * AST] << valid;
+                }
+                wb[m] = x;
+                n += L.step_n; e += L.step_e;
+                if (e >= PB) { e -= PB; n += 1; }
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: bits -> floats, streaming stores ---------------------------------------------------------
+        float *dst = obs + ((size_t)w * N + c0) * PB;
+        if (VEC4) {
+            const int n4 = TB >> 2;
+            const int sh = (lane & 7) << 2;
+            const uint32_t *wp = wb + (lane >> 3);
+            float *d4 = dst + (lane << 2);
+#pragma unroll 4
+            for (int q = lane; q < n4; q += 32, wp += 4, d4 += 128) {
+                const uint4 val = lut[(*wp >> sh) & 15u];
+                st_stream_v4(d4, val.x, val.y, val.z, val.w);
+            }
+        } else {
+            for (int f = lane; f < TB; f += 32) dst[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 1.0f : 0.0f;
+        }
+        __syncwarp();
+    }
+}
+
 // One world's observations by one warp.  `pw_reg` / `gw_reg`: cell and goal of agent `lane` (agents >= 32 are read
 // from HBM); (nr, nc) = human.getNextPos(); the obstacle bit rows are already staged in m.obits and m.abits / m.grid
 // are clean on entry.  On exit they are clean again unless L.alias (then the caller re-zeroes them for the next world).
@@ -101,11 +246,8 @@ __device__ __forceinline__ void observe_world(const EnvView &v, const ObsLayout 
                                               const int w, const int lane, const uint32_t pw_reg, const uint32_t gw_reg,
                                               const int nr, const int nc, float *__restrict__ obs,
                                               float *__restrict__ vec) {
-    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW;
-    const int F = F_T > 0 ? F_T : v.F, C = C_T > 0 ? C_T : v.C, half = F >> 1;
-    const int FF = F * F, PB = (C_T > 0 && F_T > 0) ? C_T * F_T * F_T : L.PB, AST = L.AST, CH = L.CH;
-    uint32_t *const obits = m.obits, *const abits = m.abits, *const sgoal = m.sgoal, *const spos = m.spos,
-                    *const aw = m.aw, *const wb = m.wb;
+    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW, CH = L.CH;
+    uint32_t *const abits = m.abits, *const sgoal = m.sgoal, *const spos = m.spos;
     uint8_t *const grid = m.grid;
     {
         const uint32_t *posw = reinterpret_cast<const uint32_t *>(v.pos) + (size_t)w * N;
@@ -122,136 +264,8 @@ __device__ __forceinline__ void observe_world(const EnvView &v, const ObsLayout 
         if (v.use_da | v.use_hp) { if (v.dims) { rows = v.dims[2 * w]; cols = v.dims[2 * w + 1]; } }
         __syncwarp();
 
-        for (int c0 = 0; c0 < N; c0 += CH) {
-            const int nch = min(CH, N - c0);
-            const int i = c0 + lane;
-            const bool act = lane < nch;
-            // ---- phase 1: per-agent bit strings -------------------------------------------------------------------
-            if (act) {
-                uint32_t *my = aw + lane * AST;
-                const uint32_t pw = spos[i], gw = sgoal[i];
-                const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
-                const int gr = (int16_t)(gw & 0xffff), gc = (int16_t)(gw >> 16);
-                const int top = r - half, left = c - half;                                    // :251
-                const int off = left + P;
-                if (F_T > 0) {
-                    // channels 0 and 1 accumulate in registers at compile-time bit positions
-                    constexpr int FT = F_T > 0 ? F_T : 1;
-                    constexpr int NACC = (2 * FT * FT + 31) / 32 + 1;
-                    uint32_t acc[NACC];
-#pragma unroll
-                    for (int k = 0; k < NACC; ++k) acc[k] = 0;
-#pragma unroll
-                    for (int y = 0; y < FT; ++y) {
-                        const int prow = top + y + P;
-                        uint32_t o = row_window(obits + prow * RW, off, FT);      // OOB or obstacle  (:270-276)
-                        uint32_t g = row_window(abits + prow * RW, off, FT);      // agents           (:278-285)
-                        if (y == FT / 2) { o |= 1u << (FT / 2); g &= ~(1u << (FT / 2)); }   // own cell -> channel 0 (:278-280)
-                        constexpr int dummy = 0; (void)dummy;
-                        const int p0 = y * FT, p1 = FT * FT + y * FT;
-                        acc[p0 >> 5] |= o << (p0 & 31);
-                        if ((p0 & 31) + FT > 32) acc[(p0 >> 5) + 1] |= o >> (32 - (p0 & 31));
-                        acc[p1 >> 5] |= g << (p1 & 31);
-                        if ((p1 & 31) + FT > 32) acc[(p1 >> 5) + 1] |= g >> (32 - (p1 & 31));
-                    }
-#pragma unroll
-                    for (int k = 0; k < NACC; ++k) my[k] = acc[k];
-                    for (int k = NACC; k < AST; ++k) my[k] = 0;
-                } else {
-                    for (int k = 0; k < AST; ++k) my[k] = 0;
-                    for (int y = 0; y < F; ++y) {
-                        const int prow = top + y + P;
-                        uint32_t o = row_window(obits + prow * RW, off, F);
-                        uint32_t g = row_window(abits + prow * RW, off, F);
-                        if (y == half) { o |= 1u << half; g &= ~(1u << half); }
-                        or_bits(my, y * F, o, F);
-                        or_bits(my, FF + y * F, g, F);
-                    }
-                }
-                // channel 3: goals of the agents visible in the window, clamped into it (:302-308)
-                for (int y = 0; y < F; ++y) {
-                    const int prow = top + y + P;
-                    uint32_t g = row_window(abits + prow * RW, off, F);
-                    if (y == half) g &= ~(1u << half);
-                    while (g) {
-                        const int x = __ffs(g) - 1; g &= g - 1;
-                        const int j = grid[prow * GS + off + x] - 1;
-                        const uint32_t jw = sgoal[j];
-                        const int jr = (int16_t)(jw & 0xffff), jc = (int16_t)(jw >> 16);
-                        const int mr = max(top, min(top + F - 1, jr)), mc = max(left, min(left + F - 1, jc));
-                        or_bit(my, 3 * FF + (mr - top) * F + (mc - left));
-                    }
-                }
-                if (v.use_da) {                                              // danger disc |cell - H'| <= 5 (:289-290)
-                    for (int y = 0; y < F; ++y) {
-                        const int rr = top + y, dy = rr > nr ? rr - nr : nr - rr;
-                        if (rr >= 0 && rr < rows && dy <= 5) {
-                            const int hw = dy == 0 ? 5 : dy <= 3 ? 4 : dy == 4 ? 3 : 0;
-                            const int lo = max(max(nc - hw, 0), left), hi = min(min(nc + hw, cols - 1), left + F - 1);
-                            if (lo <= hi) or_bits(my, 4 * FF + y * F + (lo - left), (1u << (hi - lo + 1)) - 1u, hi - lo + 1);
-                        }
-                    }
-                }
-                if (gr >= top && gr < top + F && gc >= left && gc < left + F)                  // own goal (:298-300)
-                    or_bit(my, 2 * FF + (gr - top) * F + (gc - left));
-                if (nr >= top && nr < top + F && nc >= left && nc < left + F)                  // human (:310-312)
-                    or_bit(my, 4 * FF + (nr - top) * F + (nc - left));
-                if (v.use_hp && C == 6 && v.hp5) {                                             // (:293-297)
-                    const int tick = v.htick[w];
-                    const int16_t *p5 = v.hp5 + (v.hp5_per_tick ? ((size_t)w * v.L + tick) * 10 : (size_t)w * 10);
-                    for (int k = 0; k < 5; ++k) {
-                        const int pr = p5[2 * k], pc = p5[2 * k + 1];
-                        if (pr >= 0 && pr < rows && pc >= 0 && pc < cols && pr >= top && pr < top + F && pc >= left && pc < left + F)
-                            or_bit(my, 5 * FF + (pr - top) * F + (pc - left));
-                    }
-                }
-                // vector (:316-323): f64 sqrt / divide, then cast
-                const double dx = (double)(gr - r), dy_ = (double)(gc - c);
-                const double d = sqrt(dx * dx + dy_ * dy_);
-                float4 o4;
-                o4.x = (float)(d != 0.0 ? dx / d : dx);
-                o4.y = (float)(d != 0.0 ? dy_ / d : dy_);
-                o4.z = (float)d;
-                o4.w = 0.0f;
-                reinterpret_cast<float4 *>(vec)[(size_t)w * N + i] = o4;
-            }
-            __syncwarp();
-            // ---- phase 1b: compact to one contiguous bit string (word m <- 32 bits starting at agent n, bit e) --------
-            const int TB = nch * PB;
-            const int nwords = (TB + 31) >> 5;
-            {
-                int n = (lane << 5) / PB, e = (lane << 5) - n * PB;
-                for (int m = lane; m < nwords; m += 32) {
-                    const uint32_t *src = aw + n * AST;
-                    uint32_t x = __funnelshift_r(src[e >> 5], src[(e >> 5) + 1], e & 31);
-                    const int valid = PB - e;
-                    if (valid < 32) {
-                        x &= (1u << valid) - 1u;
-                        if (n + 1 < nch) x |= aw[(n + 1) * AST] << valid;
-                    }
-                    wb[m] = x;
-                    n += L.step_n; e += L.step_e;
-                    if (e >= PB) { e -= PB; n += 1; }
-                }
-            }
-            __syncwarp();
-            // ---- phase 2: bits -> floats, streaming stores ---------------------------------------------------------
-            float *dst = obs + ((size_t)w * N + c0) * PB;
-            if (VEC4) {
-                const int n4 = TB >> 2;
-                const int sh = (lane & 7) << 2;
-                const uint32_t *wp = wb + (lane >> 3);
-                float *d4 = dst + (lane << 2);
-#pragma unroll 4
-                for (int q = lane; q < n4; q += 32, wp += 4, d4 += 128) {
-                    const uint4 val = lut[(*wp >> sh) & 15u];
-                    st_stream_v4(d4, val.x, val.y, val.z, val.w);
-                }
-            } else {
-                for (int f = lane; f < TB; f += 32) dst[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 1.0f : 0.0f;
-            }
-            __syncwarp();
-        }
+        for (int c0 = 0; c0 < N; c0 += CH)
+            observe_chunk<C_T, F_T, VEC4>(v, L, m, lut, w, lane, c0, min(CH, N - c0), nr, nc, rows, cols, obs, vec);
         if (!L.alias) {
             // un-scatter this world's agents so the next world starts from a clean grid
             for (int i = lane; i < N; i += 32) {
