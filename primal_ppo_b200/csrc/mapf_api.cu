@@ -356,6 +356,9 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
     CU(do_step(e, e->d_actions, nullptr, o, MODE_FUSED, s));
     // The per-agent step results are final once step_kernel has run: copy them to the host on a second stream while
     // observe_kernel writes the observations (the copy engine and the SMs overlap; ~25 MB over PCIe vs ~0.7 ms of stores).
+    // Measured alternatives at 65 536 x 32 agents: this split 0.97 ms per call; the fused kernel followed by the copies
+    // 1.33 ms (the copy is exposed); the fused kernel pipelined over four world ranges 1.18 ms (short launches lose the
+    // prefetch and tail efficiency).  Hence the two-kernel form here, the fused launch for device-resident callers.
     cudaStream_t cs = e->copy_stream;
     CU(cudaEventRecord(e->ev_step, s));
     CU(cudaStreamWaitEvent(cs, e->ev_step, 0));

@@ -285,6 +285,27 @@ def test_gpu_host_buffer_call_equals_device_call():
         assert torch.equal(obs1.cpu(), hb["obs"]) and torch.equal(vec1.cpu(), hb["vec"])
 
 
+def test_gpu_host_buffer_call_large_batch_equals_fused_device_call():
+    """The host-buffer call (two kernels, results copied back on a second stream while the observations are written)
+    against the fused device call on a larger batch: every output and the state must be equal."""
+    W, N = 16500, 4            # not a multiple of the range size
+    sc = random_scenario(W, 10, 10, N, density=(0.1, 0.25), queue_len=3, seed=77, unique_maps=128)
+    a = random_actions(5, W, N, seed=8)
+    e1, e2 = _env(sc, use_tape=False, seed=5), _env(sc, use_tape=False, seed=5)
+    hb = e2.make_host_buffers(with_obs=False, with_train_valid=True)
+    obs2 = torch.empty((W, N, 6, 9, 9), device="cuda")
+    vec2 = torch.empty((W, N, 4), device="cuda")
+    for t in range(5):
+        o1, obs1, vec1 = e1.step_observe(torch.from_numpy(a[t]))
+        hb["actions"].copy_(torch.from_numpy(a[t]))
+        e2.step_observe_host(hb, obs2, vec2)
+        for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals"):
+            _eq(_np(getattr(o1, key)), hb[key].numpy(), f"t={t} {key}")
+        assert torch.equal(obs1, obs2) and torch.equal(vec1, vec2), t
+    s1, s2 = e1.state(), e2.state()
+    assert all(torch.equal(s1[k], s2[k]) for k in s1) and torch.equal(e1.counters(), e2.counters())
+
+
 def test_gpu_full_size_properties_65536x40x40x32():
     """BASELINE.json configs[2] at full size: properties that do not need the oracle."""
     W, N, H = 65536, 32, 40

@@ -46,7 +46,7 @@ def main():
     sc = random_scenario(W, args.size, args.size, N, density=(0.0, 0.3), queue_len=16, seed=500 + rank, unique_maps=min(W, 128))
     env = BatchedMapfGym(sc, device=dev, seed=1234, use_tape=False, world_offset=rank * W)
     torch.manual_seed(0)                                  # identical initial weights on every rank
-    pol = ScrimpPolicy().to(dev)
+    pol = ScrimpPolicy().to(dev).use_channels_last()
     cfg = PPOConfig(n_steps=T, n_epochs=1)
     amp = None if args.fp32 else torch.bfloat16
     tr = VecPPOTrainer(env, pol, cfg, group=group, amp_dtype=amp, rows_per_minibatch=args.rows, seed=1234 + rank)
