@@ -266,12 +266,11 @@ def main():
     host_ring = [r.cpu().pin_memory() for r in ring]
     Ke = max(3, min(K, 20))
     for i in range(3):
-        hb["actions"].copy_(host_ring[i % 8]); env.step_observe_host(hb, obs, vec)
+        env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])
     barrier()
     t0 = time.perf_counter()
     for i in range(Ke):
-        hb["actions"].copy_(host_ring[i % 8])                        # the runner's host-side action array
-        h2d, d2h = env.step_observe_host(hb, obs, vec)
+        h2d, d2h = env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])   # the runner's pinned host action array
         _ = float(hb["reward"][0, 0])                                # the step's result is read on the host
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0

@@ -270,8 +270,11 @@ class BatchedMapfGym:
         return hb
 
     def step_observe_host(self, hb: dict, obs_dev: torch.Tensor, vec_dev: torch.Tensor,
-                          train_valid_dev: Optional[torch.Tensor] = None):
-        """actions (host) -> H2D -> step -> observe -> results D2H, synchronised.  Returns bytes moved (h2d, d2h)."""
+                          train_valid_dev: Optional[torch.Tensor] = None, actions: Optional[torch.Tensor] = None):
+        """actions (host) -> H2D -> step -> observe -> results D2H, synchronised.  Returns bytes moved (h2d, d2h).
+        `actions`: an int8 [W,N] HOST tensor (ideally pinned) to read the joint action from; default ``hb["actions"]``."""
+        act = hb["actions"] if actions is None else actions
+        assert not act.is_cuda and act.dtype == torch.int8 and act.is_contiguous() and act.numel() == self.W * self.N
         tvh = hb.get("train_valid")
         so = _cabi.MapfStepOutHost(status=hb["status"].data_ptr(), reward=hb["reward"].data_ptr(),
                                    cost=hb["cost"].data_ptr(), train_valid=None if tvh is None else tvh.data_ptr(),
@@ -280,7 +283,7 @@ class BatchedMapfGym:
         oh = hb.get("obs")
         vh = hb.get("vec")
         tvd = self._out.train_valid if train_valid_dev is None else train_valid_dev
-        _cabi.check(self._lib.mapf_step_observe_host(self._h, _ptr(hb["actions"]), C.byref(so), _ptr(obs_dev),
+        _cabi.check(self._lib.mapf_step_observe_host(self._h, _ptr(act), C.byref(so), _ptr(obs_dev),
                                                      _ptr(vec_dev), _ptr(tvd), _ptr(oh), _ptr(vh), self._stream()),
                     "mapf_step_observe_host")
         h2d = hb["actions"].numel()
