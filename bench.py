@@ -66,50 +66,108 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in-process (nvidia_ml_py) every 2 ms from a
+    background thread; falls back to an `nvidia-smi -lms` child when NVML is unavailable.  Start it before the warm-up
+    (`start()`), bracket the timed region with `mark_begin()` / `mark_end()`; `summary()` uses the samples in between."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.stop = threading.Event()
+        self.t0 = self.t1 = None
+        self.source = None
 
-    def __enter__(self):
+    def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ent = vis.split(",")[idx].strip()
+                idx = int(ent) if ent.isdigit() else idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            R = pynvml
+            bits = (("hw_slowdown", getattr(R, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                    ("hw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                    ("sw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                    ("sw_power_cap", getattr(R, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+            get_reasons = getattr(R, "nvmlDeviceGetCurrentClocksEventReasons", None) or R.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop.is_set():
+                    try:
+                        sm = float(R.nvmlDeviceGetClockInfo(h, R.NVML_CLOCK_SM))
+                        rs = int(get_reasons(h))
+                        self.rows.append((time.perf_counter(), sm, mx, [n for n, b in bits if rs & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
+            self.source = "nvml"
         except Exception:
-            self.proc = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._read_smi, daemon=True)
+                self.thread.start()
+                self.source = "nvidia-smi"
+            except Exception:
+                self.proc = None
         return self
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                reasons = [n for n, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6])
+                           if val.lower().startswith("active")]
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]), reasons))
+            except Exception:
+                continue
 
-    def __exit__(self, *a):
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def close(self):
+        self.stop.set()
         if self.proc is not None:
-            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
 
+    # context-manager form: the whole `with` body is the timed region
+    def __enter__(self):
+        if self.thread is None:
+            self.start()
+        self.mark_begin()
+        return self
+
+    def __exit__(self, *a):
+        self.mark_end()
+        time.sleep(0.01)
+        self.close()
+
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        rows = self.rows
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        if not inside and rows and self.t0 is not None:       # region shorter than the sampling period: nearest samples
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "reasons": reasons, "samples": len(inside), "source": self.source}
 
 
 def build_scenario(worlds, seed):
@@ -223,11 +281,12 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---------------- device-resident throughput (value): one fused step+observe launch per step ------------------
+    clk = ClockSampler(local_rank).start()          # running before the warm-up so that it has samples in the timed region
     for i in range(Wu):
         env.step_observe(ring[i % 8], obs_out=(obs, vec))
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     barrier()
-    with ClockSampler(local_rank) as clk:
+    with clk:
         t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
         t_start.record()
         for i in range(K):

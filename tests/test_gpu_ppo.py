@@ -44,7 +44,7 @@ def test_gpu_rollout_collect_matches_oracle_replay_and_update_runs():
     sc = random_scenario(W, 12, 12, N, density=(0.05, 0.2), queue_len=4, seed=8)
     env = BatchedMapfGym(sc, use_tape=False, seed=1)
     torch.manual_seed(0)
-    pol = ScrimpPolicy().cuda().eval()
+    pol = ScrimpPolicy().cuda().eval().use_channels_last()
     cfg = PPOConfig(n_steps=T, n_epochs=2, minibatch_size=16)
     tr = VecPPOTrainer(env, pol, cfg, rows_per_minibatch=16, seed=11)
     perf = tr.collect()
