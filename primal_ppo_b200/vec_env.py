@@ -221,6 +221,8 @@ class BatchedMapfGym:
             shape = (n, self.H, self.Wd)
         if out is None:
             out = torch.empty(shape, dtype=torch.int16, device=self.device)
+        if n == 0:                         # an empty list is not the C ABI's NULL (= all agents)
+            return out
         _cabi.check(self._lib.mapf_bfs(self._h, _ptr(lst), n, _ptr(out), self._stream()), "mapf_bfs")
         return out
 
@@ -298,10 +300,14 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, last_values: torch.Tensor, 
     assert rewards.is_cuda and rewards.dtype == torch.float32 and values.dtype == torch.float32
     r, v, lv = rewards.contiguous(), values.contiguous(), last_values.contiguous().to(torch.float32)
     T = int(r.shape[0])
-    cols = int(r.numel() // max(T, 1))
+    cols = 1
+    for d in r.shape[1:]:
+        cols *= int(d)
     assert v.shape == r.shape and lv.numel() == cols
     ret = torch.empty_like(r)
     adv = torch.empty_like(r) if return_advantages else None
+    if r.numel() == 0:                      # empty rollout: nothing to scan
+        return (ret, adv) if return_advantages else ret
     nt = None if nonterminal is None else nonterminal.to(torch.uint8).contiguous()
     stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
     with torch.cuda.device(r.device):

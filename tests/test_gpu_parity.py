@@ -198,6 +198,33 @@ def test_gpu_matches_oracle_config5_shape_80x80x128():
     _run_vs_oracle(sc, T=32, check_obs_every=4)
 
 
+def test_gpu_maximum_sizes_and_empty_inputs():
+    """The limits include/mapf_b200.h states: 128x128 cells, 128 agents for the joint step, 254 for observe / BFS;
+    empty work lists are accepted; sizes beyond the limits are refused with an error code, not a crash."""
+    from primal_ppo_b200 import BatchedMapfGym, gae
+    from primal_ppo_b200._cabi import MapfError
+    sc = random_scenario(3, 128, 128, 128, density=(0.0, 0.25), queue_len=3, seed=71, fov=31)
+    _run_vs_oracle(sc, T=6)
+    sc = random_scenario(2, 128, 128, 254, density=(0.0, 0.2), queue_len=2, seed=72, fov=9, use_da=True, use_hp=True)
+    orc = OracleMapfGym(sc, threads=8, use_tape=False)
+    env = _env(sc, use_tape=False)
+    o_obs, o_vec = orc.getAllObservations()
+    obs, vec = env.getAllObservations()
+    assert torch.equal(obs, torch.from_numpy(o_obs).cuda()) and torch.equal(vec, torch.from_numpy(o_vec).cuda())
+    _eq(_np(env.bfs_maps()), orc.bfs_maps(), "bfs 128x128x254")
+    with pytest.raises(MapfError):                       # joint step beyond 128 agents is refused, not mis-computed
+        env.step(torch.zeros((2, 254), dtype=torch.int8))
+    # empty inputs
+    empty = env.bfs_maps(agent_ids=torch.zeros((0,), dtype=torch.int32, device="cuda"))
+    assert empty.shape == (0, 128, 128)
+    r = gae(torch.zeros((0, 8), device="cuda"), torch.zeros((0, 8), device="cuda"), torch.zeros((8,), device="cuda"))
+    assert r.shape == (0, 8)
+    with pytest.raises(MapfError):
+        BatchedMapfGym(random_scenario(1, 8, 8, 2, seed=1, fov=33))       # fov must be <= 31
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((3, 254), dtype=torch.int8))                  # wrong shape (mapf_gym.py:437 assert)
+
+
 def test_gpu_sharded_worlds_equal_unsharded():
     """World w gives the same bits whichever rank owns it: run worlds [0,W) in one env and as two shards
     (world_offset keys the Philox draws), compare every output."""
