@@ -144,9 +144,10 @@ __device__ __forceinline__ void finish_work(int *counter, int total_warps, int l
 // the TMA unit to pull the state of worlds [w1 + ahead, w1 + ahead + PFB) into L2 as a few large contiguous reads; the
 // per-world register loads that follow a few microseconds later then hit L2.
 constexpr int PFB = 256;
+__device__ __forceinline__ int prefetch_batch(const EnvView &v) { return PFB << ((v.dbg_flags >> 8) & 7); }
 __device__ __forceinline__ void prefetch_world_batch(const EnvView &v, const int8_t *actions, int w0, uint64_t pol) {
     if (w0 >= v.W) return;
-    const size_t n = (size_t)min(PFB, v.W - w0), wn = (size_t)w0 * v.N, nn = n * v.N;
+    const size_t n = (size_t)min(prefetch_batch(v), v.W - w0), wn = (size_t)w0 * v.N, nn = n * v.N;
     prefetch_l2_bulk(v.obst_bits + (size_t)w0 * v.HP * v.RW, n * v.HP * v.RW * 4, pol);
     prefetch_l2_bulk(reinterpret_cast<const uint32_t *>(v.pos) + wn, nn * 4, pol);
     prefetch_l2_bulk(reinterpret_cast<const uint32_t *>(v.goal) + wn, nn * 4, pol);
@@ -165,7 +166,7 @@ __device__ __forceinline__ void prefetch_world_batch(const EnvView &v, const int
 // override it in units of PFB (0xF0 mask; value 15 = prefetch off)
 __device__ __forceinline__ int prefetch_ahead(const EnvView &v) {
     const int k = (v.dbg_flags >> 4) & 15;
-    return k == 15 ? -1 : (k ? k : 4) * PFB;
+    return k == 15 ? -1 : (k ? k : 4) * prefetch_batch(v);
 }
 
 // launchers implemented in the .cu files

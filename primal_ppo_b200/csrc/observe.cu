@@ -47,7 +47,7 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
     // what lets the batched L2 prefetch run a fixed distance ahead of the loads.
     int w = claim_work(work_counter, 1, lane);
     const uint64_t pol = policy_evict_last();
-    const int pf_ahead = prefetch_ahead(v);
+    const int pf_ahead = prefetch_ahead(v), pf_batch = prefetch_batch(v);
     WorldRegs cur, nxt;
     load_world(v, w, lane, nob, pol, cur);
     const bool direct_ob = nob > OBW * 32;
@@ -56,7 +56,7 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
     while (w < v.W) {
         const int w1 = claim_work(work_counter, 1, lane);
         load_world(v, w1, lane, nob, pol, nxt);                  // in flight while this world is processed
-        if (lane == 0 && pf_ahead >= 0 && (w1 & (PFB - 1)) == 0) prefetch_world_batch(v, nullptr, w1 + pf_ahead, pol);
+        if (lane == 0 && pf_ahead >= 0 && (w1 & (pf_batch - 1)) == 0) prefetch_world_batch(v, nullptr, w1 + pf_ahead, pol);
 
         // ---- stage: clean agent rows / id grid, obstacle bit rows from registers, agents, goals ---------------------
         if (L.alias || first) {

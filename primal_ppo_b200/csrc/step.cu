@@ -43,14 +43,14 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
     }
     int w = claim_work(work_counter, 1, lane);      // claim-then-load: see observe.cu
     const uint64_t pol = policy_evict_last();
-    const int pf_ahead = prefetch_ahead(v);
+    const int pf_ahead = prefetch_ahead(v), pf_batch = prefetch_batch(v);
     StepRegs cur, nxt;
     load_step_world<MODE>(v, actions, status_in, w, lane, nob, pol, cur);
     const bool direct_ob = nob > SOBW * 32;
     while (w < v.W) {
         const int w1 = claim_work(work_counter, 1, lane);
         load_step_world<MODE>(v, actions, status_in, w1, lane, nob, pol, nxt);
-        if (lane == 0 && pf_ahead >= 0 && (w1 & (PFB - 1)) == 0) prefetch_world_batch(v, actions, w1 + pf_ahead, pol);
+        if (lane == 0 && pf_ahead >= 0 && (w1 & (pf_batch - 1)) == 0) prefetch_world_batch(v, actions, w1 + pf_ahead, pol);
         if (!direct_ob) {
 #pragma unroll
             for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < nob) s.obits[k * 32 + lane] = cur.ob[k];

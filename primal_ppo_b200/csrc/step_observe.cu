@@ -54,7 +54,7 @@ step_observe_kernel(const EnvView v, const int8_t *__restrict__ actions, const M
 
     int w = claim_work(work_counter, 1, lane);      // claim-then-load: see observe.cu
     const uint64_t pol = policy_evict_last();
-    const int pf_ahead = prefetch_ahead(v);
+    const int pf_ahead = prefetch_ahead(v), pf_batch = prefetch_batch(v);
     StepRegs cur, nxt;
     load_step_world<MODE_FUSED>(v, actions, nullptr, w, lane, nob, pol, cur);
     const bool direct_ob = nob > SOBW * 32;
@@ -63,7 +63,7 @@ step_observe_kernel(const EnvView v, const int8_t *__restrict__ actions, const M
     while (w < v.W) {
         const int w1 = claim_work(work_counter, 1, lane);
         load_step_world<MODE_FUSED>(v, actions, nullptr, w1, lane, nob, pol, nxt);   // in flight during this world
-        if (lane == 0 && pf_ahead >= 0 && (w1 & (PFB - 1)) == 0) prefetch_world_batch(v, actions, w1 + pf_ahead, pol);
+        if (lane == 0 && pf_ahead >= 0 && (w1 & (pf_batch - 1)) == 0) prefetch_world_batch(v, actions, w1 + pf_ahead, pol);
 
         if (L.alias || first) {          // the chunk bit string of the previous world overlays these when L.alias
             for (int k = lane; k < nob; k += 32) m.abits[k] = 0;
