@@ -391,6 +391,22 @@ def main():
         line_extra["gae"] = {"T": T, "cols": cols, "ms": gae_ms, "elements_per_s": T * cols / (gae_ms * 1e-3),
                              "achieved_gbs": gae_bytes / (gae_ms * 1e-3) / 1e9, "frac": gae_bytes / (gae_ms * 1e-3) / 1e9 / peak}
         del r, v, lv
+        # reset-time work (not on the step path): on-device generation of 65 536 worlds, mapf_reset
+        try:
+            from primal_ppo_b200 import generate_scenario_device
+            nw = min(Wn, 65536)
+            generate_scenario_device(256, H, WD, N, kind="density", density=(0.0, 0.3), queue_len=16, seed=1, device=dev)
+            torch.cuda.synchronize(dev)
+            a.record()
+            dsc = generate_scenario_device(nw, H, WD, N, kind="density", density=(0.0, 0.3), queue_len=16, seed=2, device=dev)
+            b.record(); torch.cuda.synchronize(dev)
+            gen_ms = a.elapsed_time(b)
+            a.record(); env.reset(); b.record(); torch.cuda.synchronize(dev)
+            line_extra["reset"] = {"worlds": nw, "generate_scenario_ms": gen_ms, "mapf_reset_ms": a.elapsed_time(b),
+                                   "generator_flagged_worlds": float(((dsc.gen_err & ~4) != 0).float().mean())}
+            del dsc
+        except Exception as ex:
+            line_extra["reset"] = {"error": str(ex)[:200]}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
