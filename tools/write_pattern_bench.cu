@@ -9,7 +9,7 @@ __device__ __forceinline__ void st_cs(float *p, uint4 v) {
 }
 
 // A: every warp owns contiguous chunks of `chunk` bytes, claimed dynamically (the observe kernel's pattern)
-template <bool CS>
+template <bool CS, bool ZERO = false>
 __global__ void warp_chunks(float *out, int nchunks, int chunk_f4, int *counter) {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -18,7 +18,7 @@ __global__ void warp_chunks(float *out, int nchunks, int chunk_f4, int *counter)
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= nchunks) break;
         float *dst = out + (size_t)c * chunk_f4 * 4 + lane * 4;
-        const uint4 v = make_uint4(c, lane, 0x3f800000u, 0);
+        const uint4 v = ZERO ? make_uint4(0, 0, 0, 0) : make_uint4(c, lane, 0x3f800000u, 0);
 #pragma unroll 4
         for (int q = lane; q < chunk_f4; q += 32, dst += 128) {
             if (CS) st_cs(dst, v); else *reinterpret_cast<uint4 *>(dst) = v;
@@ -159,6 +159,8 @@ int main() {
         }
         printf("%-44s %.3f ms  %.0f GB/s  (%s)\n", name, best, bytes / (best * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
     };
+    run("A0 warp chunks .cs, ALL ZEROS, 4 blocks/SM", [&] { warp_chunks<true, true><<<148 * 4, 256>>>(out, nchunks, chunk_f4, counter); });
+    run("A0 warp chunks .cs, ALL ZEROS, 2 blocks/SM", [&] { warp_chunks<true, true><<<148 * 2, 256>>>(out, nchunks, chunk_f4, counter); });
     for (int bps : {2, 3, 4, 6, 8}) {
         char nm[96];
         snprintf(nm, sizeof nm, "A warp chunks .cs, %d blocks/SM x 8 warps", bps);
@@ -206,15 +208,7 @@ int main() {
         cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
         printf("persistingL2CacheMaxSize %.1f MB, accessPolicyMaxWindowSize %.1f MB, L2 %.1f MB\n", prop.persistingL2CacheMaxSize / 1e6,
                prop.accessPolicyMaxWindowSize / 1e6, prop.l2CacheSize / 1e6);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize);
         cudaStream_t st; cudaStreamCreate(&st);
-        cudaStreamAttrValue attr = {};
-        attr.accessPolicyWindow.base_ptr = in;
-        attr.accessPolicyWindow.num_bytes = in_bytes;
-        attr.accessPolicyWindow.hitRatio = 1.0f;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
         auto runs = [&](const char *name, auto launch) {
             float best = 1e9;
             for (int it = 0; it < 6; ++it) {
@@ -222,10 +216,26 @@ int main() {
                 cudaEventRecord(a, st); launch(); cudaEventRecord(b, st); cudaEventSynchronize(b);
                 float ms; cudaEventElapsedTime(&ms, a, b); if (it > 0 && ms < best) best = ms;
             }
-            printf("%-44s %.3f ms  %.0f GB/s  (%s)\n", name, best, bytes / (best * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
+            printf("%-60s %.3f ms  %.0f GB/s  (%s)\n", name, best, bytes / (best * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
         };
-        runs("F4 persisting window on inputs, plain ld/st", [&] { warp_chunks_prefetch<7, 0><<<148 * 4, 256, sm, st>>>(out, nchunks, chunk_f4, counter, in); });
-        runs("F5 persisting window + .cs stores", [&] { warp_chunks_prefetch<7, 1><<<148 * 4, 256, sm, st>>>(out, nchunks, chunk_f4, counter, in); });
+        // persisting-L2 set-aside sweep: how much of L2 can be reserved for the 58.7 MB of inputs before the write stream suffers?
+        for (size_t mb : {(size_t)0, (size_t)8, (size_t)16, (size_t)24, (size_t)32, (size_t)48, (size_t)64}) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, mb << 20);
+            cudaStreamAttrValue attr = {};
+            attr.accessPolicyWindow.base_ptr = in;
+            attr.accessPolicyWindow.num_bytes = mb ? in_bytes : 0;
+            attr.accessPolicyWindow.hitRatio = mb ? (float)((double)(mb << 20) / (double)in_bytes > 1.0 ? 1.0 : (double)(mb << 20) / (double)in_bytes) : 0.f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+            char nm[128];
+            snprintf(nm, sizeof nm, "F4 set-aside %zu MB, window on 58.7 MB inputs, plain ld/st", mb);
+            runs(nm, [&] { warp_chunks_prefetch<7, 0><<<148 * 4, 256, sm, st>>>(out, nchunks, chunk_f4, counter, in); });
+            snprintf(nm, sizeof nm, "   same set-aside, pure write stream (pattern A, 4 blk/SM)");
+            runs(nm, [&] { warp_chunks<true><<<148 * 4, 256, 0, st>>>(out, nchunks, chunk_f4, counter); });
+        }
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        cudaCtxResetPersistingL2Cache();
     }
     for (int bps : {4, 8, 16}) {
         char nm[96];
