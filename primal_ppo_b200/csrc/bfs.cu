@@ -35,7 +35,7 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
     constexpr int MPW = 32 / G;                                   // maps per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, gl = lane % G;                      // map slot within the warp, lane within the map
-    const int H = v.H, Wd = v.Wd, P = v.P, RW = v.RW;
+    const int H = v.H, Wd = v.Wd;
     int16_t *tile = reinterpret_cast<int16_t *>(smem_raw + ((size_t)warp * MPW + grp) * tile_bytes);
     const int cells = H * Wd;
     const long long n_maps = n_dev ? (long long)*n_dev : n_maps_in;   // device-side count: no host sync for refreshes
@@ -56,20 +56,19 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
             for (int k = gl; k < (cells + 1) / 2; k += G) t32[k] = 0xffffffffu;
         }
         uint32_t freeb[R][NW], vis[R][NW], fr[R][NW];
-        const uint32_t *ob = v.obst_bits + (size_t)w * v.HP * RW;
+        const uint32_t *ob = v.obst_pack + (size_t)w * v.PW;          // packed bit matrix, bit r*Wd + c
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int r = gl * R + k;
 #pragma unroll
             for (int q = 0; q < NW; ++q) {
                 uint32_t x = 0;
-                if (r < H && valid) {
-                    const uint32_t *row = ob + (size_t)(r + P) * RW;
-                    const int i0 = q + (P >> 5);
-                    const uint32_t lo = i0 < RW ? __ldg(row + i0) : 0xffffffffu, hi = i0 + 1 < RW ? __ldg(row + i0 + 1) : 0xffffffffu;
-                    x = ~__funnelshift_r(lo, hi, P & 31);
-                    const int nb = Wd - 32 * q;
-                    if (nb < 32) x &= nb > 0 ? ((1u << nb) - 1u) : 0u;
+                const int nb = Wd - 32 * q;
+                if (r < H && valid && nb > 0) {
+                    const int n = nb < 32 ? nb : 32, off = r * Wd + 32 * q, kk = off >> 5;
+                    const uint32_t lo = __ldg(ob + kk), hi = (kk + 1 < v.PW) ? __ldg(ob + kk + 1) : 0u;
+                    x = ~__funnelshift_r(lo, hi, off & 31);
+                    if (n < 32) x &= (1u << n) - 1u;
                 }
                 freeb[k][q] = x;
                 const bool here = (r == goal_r) && ((goal_c >> 5) == q);

@@ -1,8 +1,12 @@
 // common.cuh — shared device-side definitions of the B200 MAPF hot path (sm_100a).
 //
 // HBM layout (all env-owned buffers are SoA over worlds, allocated once in mapf_create):
-//   obst_bits u32 [W, HP, RW]  obstacle / out-of-bounds bit rows, padded by P cells on every side (1 = blocked);
-//                              HP = H + 2P rows, row bit (c + P) is cell c.  384 B per 40x40 world instead of 1600 B.
+//   obst_pack u32 [W, PW]      the obstacle map as a tightly packed bit matrix, bit r*Wd + c (1 = blocked, incl. cells
+//                              outside a world's dims); PW words, a multiple of 4.  208 B per 40x40 world instead of
+//                              1600 B.  Kernels expand it in shared memory into rows padded by P cells on every side
+//                              (HP = H + 2P rows of RW words, row bit c + P is cell c): the expansion is ALU work, which
+//                              is free next to the observation store, and every byte NOT read from HBM while 4 GB of
+//                              stores drain is worth ~50 bytes of write bandwidth.
 //   pos, goal i16 [W,N,2]      agent cell and current goal (row, col)
 //   rep       i8  [W,N]        Agent.invalidActions[2]: the one repetition action, -1 when empty (mapf_gym.py:158-161)
 //   qcur      i32 [W,N]        goals already handed out from goal_queue (Sequence.curIdx - 1, util.py:33-39)
@@ -27,7 +31,8 @@ constexpr int ST_STATIC = -1, ST_HUMAN = -2, ST_AGENT = -3, ST_REPEAT = -4, ST_O
 
 struct EnvView {
     int W, H, Wd, N, F, C, use_da, use_hp, Q, L, TL, hp5_per_tick;
-    int P;        // padding of obst_bits / the agent-id grid = max(2, F/2)
+    int P;        // padding of the shared-memory bit rows / the agent-id grid = max(2, F/2)
+    int PW;       // u32 words of one world's packed obstacle bit matrix (multiple of 4)
     int HP;       // H + 2P
     int RW;       // u32 words per padded bit row (+1 spare word so a funnel read of word k+1 is always in range)
     int GS;       // byte stride of one row of the shared-memory agent-id grid (multiple of 16)
@@ -40,7 +45,7 @@ struct EnvView {
     const int32_t *hlen, *tape_len;
     const int8_t *tape;
     // owned state
-    uint32_t *obst_bits;
+    uint32_t *obst_pack;
     int16_t *pos, *goal;
     int8_t *rep;
     int32_t *qcur, *htick, *tape_cur, *nstep;
@@ -61,6 +66,35 @@ __device__ __forceinline__ uint32_t row_window(const uint32_t *row, int off, int
     return v & ((1u << nbits) - 1u);
 }
 __device__ __forceinline__ uint32_t row_bit(const uint32_t *row, int off) { return (row[off >> 5] >> (off & 31)) & 1u; }
+
+// ---- packed obstacle bit matrix -> padded bit rows ---------------------------------------------------------------
+// bits [off, off + n), n <= 32, of a packed bit array of `nwords` words
+__device__ __forceinline__ uint32_t pack_extract(const uint32_t *p, int off, int n, int nwords) {
+    const int k = off >> 5;
+    const uint32_t lo = p[k], hi = (k + 1 < nwords) ? p[k + 1] : 0u;
+    const uint32_t x = __funnelshift_r(lo, hi, off & 31);
+    return n >= 32 ? x : (x & ((1u << n) - 1u));
+}
+// word q of padded row pr: 1 = obstacle or out of bounds
+__device__ __forceinline__ uint32_t padded_row_word(const uint32_t *packed, int H, int Wd, int P, int PW, int pr, int q) {
+    const int r = pr - P;
+    if (r < 0 || r >= H) return 0xffffffffu;
+    const int c0 = 32 * q - P;                                   // column held by bit 0 of this word
+    const int lo = c0 > 0 ? c0 : 0, hi = c0 + 32 < Wd ? c0 + 32 : Wd;
+    if (hi <= lo) return 0xffffffffu;
+    const int n = hi - lo, sh = lo - c0;
+    const uint32_t bits = pack_extract(packed, r * Wd + lo, n, PW);
+    const uint32_t mask = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << sh;
+    return (bits << sh) | ~mask;
+}
+// all `nthreads` threads of a warp / CTA expand one world (packed may live in shared or global memory)
+__device__ __forceinline__ void expand_obstacle_rows(uint32_t *obits, const uint32_t *packed, const EnvView &v, int tid, int nthreads) {
+    const int nob = v.HP * v.RW;
+    for (int k = tid; k < nob; k += nthreads) {
+        const int pr = k / v.RW;
+        obits[k] = padded_row_word(packed, v.H, v.Wd, v.P, v.PW, pr, k - pr * v.RW);
+    }
+}
 
 // Philox4x32-10, counter = (world, step, draw, tag), key = seed: the stand-in for Python's `random.choice`
 // (mapf_gym.py:588) when the caller supplies no tape.  Bit-identical to the oracle's philox_draw.
@@ -148,7 +182,7 @@ __device__ __forceinline__ int prefetch_batch(const EnvView &v) { return PFB << 
 __device__ __forceinline__ void prefetch_world_batch(const EnvView &v, const int8_t *actions, int w0, uint64_t pol) {
     if (w0 >= v.W) return;
     const size_t n = (size_t)min(prefetch_batch(v), v.W - w0), wn = (size_t)w0 * v.N, nn = n * v.N;
-    prefetch_l2_bulk(v.obst_bits + (size_t)w0 * v.HP * v.RW, n * v.HP * v.RW * 4, pol);
+    prefetch_l2_bulk(v.obst_pack + (size_t)w0 * v.PW, n * v.PW * 4, pol);
     prefetch_l2_bulk(reinterpret_cast<const uint32_t *>(v.pos) + wn, nn * 4, pol);
     prefetch_l2_bulk(reinterpret_cast<const uint32_t *>(v.goal) + wn, nn * 4, pol);
     prefetch_l2_bulk(reinterpret_cast<const int2 *>(v.hcur) + w0, n * 8, pol);

@@ -47,21 +47,21 @@ static int cuda_fail(cudaError_t e, const char *what) {
 namespace mapf {
 namespace {
 
-// populateMap (mapf_gym.py:175-184) + packing of the obstacle map into padded bit rows. One warp per world.
+// populateMap (mapf_gym.py:175-184) + packing of the obstacle map into a bit matrix. One warp per world.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) reset_kernel(const EnvView v) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (w >= v.W) return;
     const int rows = v.dims ? v.dims[2 * w] : v.H, cols = v.dims ? v.dims[2 * w + 1] : v.Wd;
     const uint8_t *ob = v.obst + (size_t)w * v.H * v.Wd;
-    uint32_t *dst = v.obst_bits + (size_t)w * v.HP * v.RW;
-    for (int k = lane; k < v.HP * v.RW; k += 32) {
-        const int pr = k / v.RW, q = k - pr * v.RW;
-        const int r = pr - v.P;
+    uint32_t *dst = v.obst_pack + (size_t)w * v.PW;
+    const int cells = v.H * v.Wd;
+    for (int k = lane; k < v.PW; k += 32) {
         uint32_t bits = 0;
         for (int b = 0; b < 32; ++b) {
-            const int c = q * 32 + b - v.P;
-            const bool blocked = r < 0 || r >= rows || c < 0 || c >= cols || ob[r * v.Wd + c] != 0;
+            const int idx = k * 32 + b;
+            const int r = idx / v.Wd, c = idx - r * v.Wd;
+            const bool blocked = idx >= cells || r >= rows || c >= cols || ob[idx] != 0;
             bits |= (blocked ? 1u : 0u) << b;
         }
         dst[k] = bits;
@@ -120,10 +120,11 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
     v.HP = v.H + 2 * v.P;
     v.RW = (v.Wd + 2 * v.P + 31) / 32 + 1;
     v.GS = ((v.Wd + 2 * v.P + 15) / 16) * 16;
+    v.PW = (((v.H * v.Wd + 31) / 32) + 3) & ~3;
     const size_t W = v.W, WN = (size_t)v.W * v.N;
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(p, bytes ? bytes : 1); };
-    alloc((void **)&v.obst_bits, W * v.HP * v.RW * 4);
+    alloc((void **)&v.obst_pack, W * v.PW * 4);
     alloc((void **)&v.pos, WN * 4);
     alloc((void **)&v.goal, WN * 4);
     alloc((void **)&v.rep, WN);
@@ -150,7 +151,7 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
 int mapf_destroy(MapfEnv *e) {
     if (!e) return MAPF_OK;
     EnvView &v = e->v;
-    cudaFree(v.obst_bits); cudaFree(v.pos); cudaFree(v.goal); cudaFree(v.rep); cudaFree(v.qcur); cudaFree(v.htick);
+    cudaFree(v.obst_pack); cudaFree(v.pos); cudaFree(v.goal); cudaFree(v.rep); cudaFree(v.qcur); cudaFree(v.htick);
     cudaFree(v.tape_cur); cudaFree(v.nstep); cudaFree(v.err); cudaFree(v.counters); cudaFree(v.hcur); cudaFree(v.hnx); cudaFree(e->d_work); cudaFree(e->d_work_bfs); cudaFree(e->d_list); cudaFree(e->d_count);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_step) cudaEventDestroy(e->ev_step);

@@ -31,7 +31,7 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint4 lut[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int GS = v.GS, HP = v.HP, nob = v.HP * v.RW;
+    const int GS = v.GS, HP = v.HP, nob = v.HP * v.RW, npw = v.PW;
     const ObsSmem m = obs_carve(smem_raw + (size_t)warp * L.total, L, v.N);
     uint32_t *const obits = m.obits, *const abits = m.abits;
     uint8_t *const grid = m.grid;
@@ -49,28 +49,31 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
     const uint64_t pol = policy_evict_last();
     const int pf_ahead = prefetch_ahead(v), pf_batch = prefetch_batch(v);
     WorldRegs cur, nxt;
-    load_world(v, w, lane, nob, pol, cur);
-    const bool direct_ob = nob > OBW * 32;
+    load_world(v, w, lane, npw, pol, cur);
+    const bool direct_ob = npw > OBW * 32;
     bool first = true;
 
     while (w < v.W) {
         const int w1 = claim_work(work_counter, 1, lane);
-        load_world(v, w1, lane, nob, pol, nxt);                  // in flight while this world is processed
+        load_world(v, w1, lane, npw, pol, nxt);                  // in flight while this world is processed
         if (lane == 0 && pf_ahead >= 0 && (w1 & (pf_batch - 1)) == 0) prefetch_world_batch(v, nullptr, w1 + pf_ahead, pol);
 
-        // ---- stage: clean agent rows / id grid, obstacle bit rows from registers, agents, goals ---------------------
+        // ---- stage: packed obstacle words (registers -> scratch in the agent-presence rows -> padded rows), then clean
+        //      agent rows / id grid
+        if (!direct_ob) {
+#pragma unroll
+            for (int k = 0; k < OBW; ++k) if (k * 32 + lane < npw) abits[k * 32 + lane] = cur.ob[k];
+            __syncwarp();
+            expand_obstacle_rows(obits, abits, v, lane, 32);
+        } else {
+            expand_obstacle_rows(obits, v.obst_pack + (size_t)w * npw, v, lane, 32);
+        }
+        __syncwarp();
+        for (int k = lane; k < nob; k += 32) abits[k] = 0;
         if (L.alias || first) {
-            for (int k = lane; k < nob; k += 32) abits[k] = 0;
             uint4 *g4 = reinterpret_cast<uint4 *>(grid);
             for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
             first = false;
-        }
-        if (!direct_ob) {
-#pragma unroll
-            for (int k = 0; k < OBW; ++k) if (k * 32 + lane < nob) obits[k * 32 + lane] = cur.ob[k];
-        } else {
-            const uint32_t *src = v.obst_bits + (size_t)w * nob;
-            for (int k = lane; k < nob; k += 32) obits[k] = __ldg(src + k);
         }
         __syncwarp();
         const int nr = (int16_t)(cur.ht.y & 0xffff), nc = (int16_t)((uint32_t)cur.ht.y >> 16);   // human.getNextPos()

@@ -52,8 +52,7 @@ observe_wide_kernel(const EnvView v, float *__restrict__ obs, float *__restrict_
         const int w = s_world;
         if (w >= v.W) break;
         // ---- stage the world once for the CTA ---------------------------------------------------------------------
-        const uint32_t *src = v.obst_bits + (size_t)w * nob;
-        for (int k = tid; k < nob; k += blockDim.x) m.obits[k] = __ldg(src + k);
+        expand_obstacle_rows(m.obits, v.obst_pack + (size_t)w * v.PW, v, tid, blockDim.x);
         const uint32_t *posw = reinterpret_cast<const uint32_t *>(v.pos) + (size_t)w * N;
         const uint32_t *goalw = reinterpret_cast<const uint32_t *>(v.goal) + (size_t)w * N;
         for (int i = tid; i < N; i += blockDim.x) {

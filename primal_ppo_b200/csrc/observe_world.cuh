@@ -9,7 +9,7 @@ namespace ow {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-constexpr int OBW = 8;   // obstacle-bit words prefetched per lane (covers HP*RW <= 256; 144 for 40x40 with F=9)
+constexpr int OBW = 4;   // packed obstacle words prefetched per lane (PW <= 128: up to 64x64 cells; 40x40 needs 52)
 
 struct ObsLayout {
     int PB;      // bits per agent = C*F*F
@@ -58,7 +58,7 @@ __device__ __forceinline__ void or_bit(uint32_t *words, int p) { words[p >> 5] |
 // inputs of one world held in registers (prefetched one world ahead)
 struct WorldRegs {
     uint32_t pw, gw;        // cell / goal of agent `lane` (agents >= 32 are loaded directly)
-    uint32_t ob[OBW];       // obstacle bit words lane, lane+32, ...
+    uint32_t ob[OBW];       // packed obstacle words lane, lane+32, ...
     int2 ht;                // human (pos, next) of the current tick
 };
 
@@ -68,7 +68,7 @@ __device__ __forceinline__ void load_world(const EnvView &v, int w, int lane, in
         const int i = lane < v.N ? lane : 0;
         r.pw = ld_keep(reinterpret_cast<const uint32_t *>(v.pos) + base + i, pol);
         r.gw = ld_keep(reinterpret_cast<const uint32_t *>(v.goal) + base + i, pol);
-        const uint32_t *src = v.obst_bits + (size_t)w * nob;
+        const uint32_t *src = v.obst_pack + (size_t)w * v.PW;
 #pragma unroll
         for (int k = 0; k < OBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? ld_keep(src + k * 32 + lane, pol) : 0u;
         r.ht = ld_keep_v2(reinterpret_cast<const int2 *>(v.hcur) + w, pol);

@@ -35,7 +35,7 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
             const MapfStepOut out, const int per_warp, int *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int HP = v.HP, RW = v.RW, GS = v.GS, nob = v.HP * v.RW;
+    const int HP = v.HP, RW = v.RW, GS = v.GS, npw = v.PW;
     WarpSmem s = carve(smem_raw + (size_t)warp * per_warp, HP, RW, GS);
     {
         uint4 *g4 = reinterpret_cast<uint4 *>(s.grid);
@@ -45,21 +45,21 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
     const uint64_t pol = policy_evict_last();
     const int pf_ahead = prefetch_ahead(v), pf_batch = prefetch_batch(v);
     StepRegs cur, nxt;
-    load_step_world<MODE>(v, actions, status_in, w, lane, nob, pol, cur);
-    const bool direct_ob = nob > SOBW * 32;
+    load_step_world<MODE>(v, actions, status_in, w, lane, npw, pol, cur);
+    const bool direct_ob = npw > SOBW * 32;
     while (w < v.W) {
         const int w1 = claim_work(work_counter, 1, lane);
-        load_step_world<MODE>(v, actions, status_in, w1, lane, nob, pol, nxt);
+        load_step_world<MODE>(v, actions, status_in, w1, lane, npw, pol, nxt);
         if (lane == 0 && pf_ahead >= 0 && (w1 & (pf_batch - 1)) == 0) prefetch_world_batch(v, actions, w1 + pf_ahead, pol);
-        if (!direct_ob) {
+        if (!direct_ob) {                       // the packed obstacle words are probed directly (resolve_world<.., true>)
 #pragma unroll
-            for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < nob) s.obits[k * 32 + lane] = cur.ob[k];
+            for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < npw) s.obits[k * 32 + lane] = cur.ob[k];
         } else {
-            const uint32_t *src = v.obst_bits + (size_t)w * nob;
-            for (int k = lane; k < nob; k += 32) s.obits[k] = __ldg(src + k);
+            const uint32_t *src = v.obst_pack + (size_t)w * npw;
+            for (int k = lane; k < npw; k += 32) s.obits[k] = __ldg(src + k);
         }
-        uint32_t npw, ngw;
-        resolve_world<MODE>(v, out, s, w, lane, cur, pol, npw, ngw);
+        uint32_t new_pw, new_gw;
+        resolve_world<MODE, true>(v, out, s, w, lane, cur, pol, new_pw, new_gw);
         __syncwarp();
         w = w1;
         cur = nxt;

@@ -27,7 +27,7 @@ step_observe_kernel(const EnvView v, const int8_t *__restrict__ actions, const M
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint4 lut[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int HP = v.HP, GS = v.GS, nob = v.HP * v.RW;
+    const int HP = v.HP, GS = v.GS, nob = v.HP * v.RW, npw = v.PW;
     unsigned char *base = smem_raw + (size_t)warp * per_warp;
     const ObsSmem m = obs_carve(base, L, v.N);
     // the step phase shares the obstacle bit rows and the agent-id grid with the observe phase; its own scratch
@@ -56,35 +56,38 @@ step_observe_kernel(const EnvView v, const int8_t *__restrict__ actions, const M
     const uint64_t pol = policy_evict_last();
     const int pf_ahead = prefetch_ahead(v), pf_batch = prefetch_batch(v);
     StepRegs cur, nxt;
-    load_step_world<MODE_FUSED>(v, actions, nullptr, w, lane, nob, pol, cur);
-    const bool direct_ob = nob > SOBW * 32;
+    load_step_world<MODE_FUSED>(v, actions, nullptr, w, lane, npw, pol, cur);
+    const bool direct_ob = npw > SOBW * 32;
     bool first = true;
 
     while (w < v.W) {
         const int w1 = claim_work(work_counter, 1, lane);
-        load_step_world<MODE_FUSED>(v, actions, nullptr, w1, lane, nob, pol, nxt);   // in flight during this world
+        load_step_world<MODE_FUSED>(v, actions, nullptr, w1, lane, npw, pol, nxt);   // in flight during this world
         if (lane == 0 && pf_ahead >= 0 && (w1 & (pf_batch - 1)) == 0) prefetch_world_batch(v, actions, w1 + pf_ahead, pol);
 
-        if (L.alias || first) {          // the chunk bit string of the previous world overlays these when L.alias
-            for (int k = lane; k < nob; k += 32) m.abits[k] = 0;
+        // packed obstacle words: registers -> scratch (the agent-presence rows, zeroed right after) -> padded rows
+        if (!direct_ob) {
+#pragma unroll
+            for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < npw) m.abits[k * 32 + lane] = cur.ob[k];
+            __syncwarp();
+            expand_obstacle_rows(m.obits, m.abits, v, lane, 32);
+        } else {
+            expand_obstacle_rows(m.obits, v.obst_pack + (size_t)w * npw, v, lane, 32);
+        }
+        __syncwarp();
+        for (int k = lane; k < nob; k += 32) m.abits[k] = 0;
+        if (L.alias || first) {          // the chunk bit string of the previous world overlays the id grid when L.alias
             uint4 *g4 = reinterpret_cast<uint4 *>(m.grid);
             for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
             first = false;
         }
-        if (!direct_ob) {
-#pragma unroll
-            for (int k = 0; k < SOBW; ++k) if (k * 32 + lane < nob) m.obits[k * 32 + lane] = cur.ob[k];
-        } else {
-            const uint32_t *src = v.obst_bits + (size_t)w * nob;
-            for (int k = lane; k < nob; k += 32) m.obits[k] = __ldg(src + k);
-        }
         __syncwarp();
-        uint32_t npw, ngw;
-        resolve_world<MODE_FUSED>(v, out, s, w, lane, cur, pol, npw, ngw);      // leaves the id grid clean
+        uint32_t new_pw, new_gw;
+        resolve_world<MODE_FUSED>(v, out, s, w, lane, cur, pol, new_pw, new_gw);      // leaves the id grid clean
         __syncwarp();
         // the human has ticked: its getNextPos() is the `next` field of the following trace entry
         const int nr = (int16_t)(cur.ht2.y & 0xffff), nc = (int16_t)((uint32_t)cur.ht2.y >> 16);
-        observe_world<C_T, F_T, VEC4>(v, L, m, lut, w, lane, npw, ngw, nr, nc, obs, vec);
+        observe_world<C_T, F_T, VEC4>(v, L, m, lut, w, lane, new_pw, new_gw, nr, nc, obs, vec);
         w = w1;
         cur = nxt;
     }

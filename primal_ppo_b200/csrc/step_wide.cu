@@ -64,8 +64,7 @@ step_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8
 
     // ---- stage ------------------------------------------------------------------------------------------------
     {
-        const uint32_t *src = v.obst_bits + (size_t)w * HP * RW;
-        for (int k = lane; k < HP * RW; k += 32) s.obits[k] = __ldg(src + k);
+        expand_obstacle_rows(s.obits, v.obst_pack + (size_t)w * v.PW, v, lane, 32);
         uint4 *g4 = reinterpret_cast<uint4 *>(s.grid);
         for (int k = lane; k < (HP * GS) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
     }

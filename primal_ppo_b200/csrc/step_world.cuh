@@ -44,14 +44,14 @@ __device__ inline WarpSmem carve(unsigned char *base, int HP, int RW, int GS) {
     return s;
 }
 
-constexpr int SOBW = 5;   // obstacle-bit words prefetched per lane (HP*RW <= 160: 40x40 with F = 9 needs 144)
+constexpr int SOBW = 4;   // packed obstacle words prefetched per lane (PW <= 128: up to 64x64 cells; 40x40 needs 52)
 
 // inputs of one world, prefetched one world ahead of the one being resolved
 struct StepRegs {
     uint32_t pw, gw;          // cell, goal of agent `lane`
     int rep, act;             // repetition action, joint action
     int st_in;                // MODE_JOINT: status computed earlier by mapf_evaluate
-    uint32_t ob[SOBW];        // obstacle bit words lane, lane+32, ...
+    uint32_t ob[SOBW];        // packed obstacle words lane, lane+32, ...
     int2 ht, ht2;             // human (pos,next) at the current tick and after this step's tick
     int tick, hlen;
 };
@@ -67,7 +67,7 @@ __device__ __forceinline__ void load_step_world(const EnvView &v, const int8_t *
         r.rep = ld_keep_s8(v.rep + idx, pol);
         r.act = __ldg(actions + idx);
         r.st_in = (MODE == MODE_JOINT) ? (int)__ldg(status_in + idx) : 0;
-        const uint32_t *src = v.obst_bits + (size_t)w * nob;
+        const uint32_t *src = v.obst_pack + (size_t)w * v.PW;
 #pragma unroll
         for (int k = 0; k < SOBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? ld_keep(src + k * 32 + lane, pol) : 0u;
         r.ht = ld_keep_v2(reinterpret_cast<const int2 *>(v.hcur) + w, pol);
@@ -77,7 +77,9 @@ __device__ __forceinline__ void load_step_world(const EnvView &v, const int8_t *
     }
 }
 
-template <int MODE>
+// PACKED_OB: s.obits holds the world's PACKED obstacle bit matrix (step_kernel: the four wall probes per agent do not
+// justify expanding padded rows); otherwise the padded bit rows (fused kernel, where the observation build needs them).
+template <int MODE, bool PACKED_OB = false>
 __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOut &out, const WarpSmem &s, const int w,
                                               const int lane, const StepRegs &in, const uint64_t pol,
                                               uint32_t &new_pw, uint32_t &new_gw) {
@@ -109,7 +111,14 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
 #pragma unroll
     for (int k = 1; k < NA; ++k) {
         const int tr = r + ((k == 2) - (k == 4)), tc = c + ((k == 1) - (k == 3));
-        if (row_bit(s.obits + (tr + P) * RW, tc + P)) inv0 |= 1u << k;                         // OOB or wall
+        bool blocked;
+        if (PACKED_OB) {
+            const int ci = tr * v.Wd + tc;
+            blocked = (unsigned)tr >= (unsigned)v.H || (unsigned)tc >= (unsigned)v.Wd || ((s.obits[ci >> 5] >> (ci & 31)) & 1u);
+        } else {
+            blocked = row_bit(s.obits + (tr + P) * RW, tc + P);
+        }
+        if (blocked) inv0 |= 1u << k;                                                          // OOB or wall
     }
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
