@@ -391,6 +391,22 @@ def main():
         line_extra["gae"] = {"T": T, "cols": cols, "ms": gae_ms, "elements_per_s": T * cols / (gae_ms * 1e-3),
                              "achieved_gbs": gae_bytes / (gae_ms * 1e-3) / 1e9, "frac": gae_bytes / (gae_ms * 1e-3) / 1e9 / peak}
         del r, v, lv
+        # optional bf16 observation format (same values, half the bytes; not the reference layout, not the headline)
+        try:
+            ob16 = torch.empty((Wn, N, CH, FOV, FOV), dtype=torch.bfloat16, device=dev)
+            for i in range(3):
+                env.step_observe(ring[i % 8], obs_out=(ob16, vec))
+            torch.cuda.synchronize(dev)
+            a.record()
+            for i in range(10):
+                env.step_observe(ring[i % 8], obs_out=(ob16, vec))
+            b.record(); torch.cuda.synchronize(dev)
+            ms16 = a.elapsed_time(b) / 10
+            line_extra["bf16_observations"] = {"ms_per_step": ms16, "agent_steps_per_s": Wn * N / (ms16 * 1e-3),
+                                               "note": "mapf_step_observe_bf16: optional output format, outside the reference layout"}
+            del ob16
+        except Exception as ex:
+            line_extra["bf16_observations"] = {"error": str(ex)[:200]}
         # reset-time work (not on the step path): on-device generation of 65 536 worlds, mapf_reset
         try:
             from primal_ppo_b200 import generate_scenario_device

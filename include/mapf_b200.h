@@ -124,6 +124,13 @@ int mapf_observe(MapfEnv *env, float *obs, float *vec, void *stream);
  * observation block that needs several chunks). */
 int mapf_step_observe(MapfEnv *env, const int8_t *actions, const MapfStepOut *out, float *obs, float *vec, void *stream);
 
+/* Optional output format (NOT the reference's layout): the same observations as bf16 [W,N,C,F,F] — every value is 0 or 1
+ * and exact in bf16 — for GPU-resident training loops whose network runs under bf16 autocast anyway (the reference casts
+ * the f32 observations to half precision at the first convolution, net.py:101).  Halves the bytes of the dominant store. */
+int mapf_observe_bf16(MapfEnv *env, uint16_t *obs_bf16, float *vec, void *stream);
+int mapf_step_observe_bf16(MapfEnv *env, const int8_t *actions, const MapfStepOut *out, uint16_t *obs_bf16, float *vec,
+                           void *stream);
+
 /* makeBfsMap (mapf_gym.py:211-244) for the CURRENT goals.  agent_list: n flat ids (w*N+i), or NULL for all W*N
  * agents in order.  out: int16 [n,H,Wd]: -1 obstacle (and cells outside a world's dims), -2 unreached, >=0 distance. */
 int mapf_bfs(MapfEnv *env, const int32_t *agent_list, int64_t n, int16_t *out, void *stream);

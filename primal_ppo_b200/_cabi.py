@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_PKG, "libmapf_b200.so")
 EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_reset", "mapf_evaluate",
             "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae",
             "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe",
-            "mapf_sample_actions", "mapf_generate_scenario"]
+            "mapf_sample_actions", "mapf_generate_scenario",
+            "mapf_observe_bf16", "mapf_step_observe_bf16"]
 
 ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE = 1, 2, 4, 8
 
@@ -73,6 +74,8 @@ def load_library():
     lib.mapf_step.argtypes = [vp, vp, C.POINTER(MapfStepOut), vp]
     lib.mapf_observe.argtypes = [vp, vp, vp, vp]
     lib.mapf_step_observe.argtypes = [vp, vp, C.POINTER(MapfStepOut), vp, vp, vp]
+    lib.mapf_observe_bf16.argtypes = [vp, vp, vp, vp]
+    lib.mapf_step_observe_bf16.argtypes = [vp, vp, C.POINTER(MapfStepOut), vp, vp, vp]
     lib.mapf_bfs.argtypes = [vp, vp, i64, vp, vp]
     lib.mapf_bfs_refresh.argtypes = [vp, vp, vp, vp]
     lib.mapf_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp, vp, vp]

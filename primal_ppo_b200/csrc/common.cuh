@@ -209,11 +209,11 @@ cudaError_t launch_step(const EnvView &v, const int8_t *actions, const int8_t *s
                         int mode, int *work_counter, cudaStream_t s);
 cudaError_t launch_step_wide(const EnvView &v, const int8_t *actions, const int8_t *status_in, const MapfStepOut &out,
                              int mode, cudaStream_t s);
-cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t s);
+cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t s, int out_bf16 = 0);
 bool step_observe_fusable(const EnvView &v);
 cudaError_t launch_step_observe(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
-                                int *work_counter, cudaStream_t s);
-cudaError_t launch_observe_wide(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t s);
+                                int *work_counter, cudaStream_t s, int out_bf16 = 0);
+cudaError_t launch_observe_wide(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t s, int out_bf16 = 0);
 cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
                        int scatter, int *work_counter, cudaStream_t s);
 cudaError_t launch_arrivals(const EnvView &v, const uint8_t *goals, int32_t *list, int32_t *n_dev, cudaStream_t s);

@@ -243,6 +243,29 @@ int mapf_step_observe(MapfEnv *e, const int8_t *actions, const MapfStepOut *out,
     return MAPF_OK;
 }
 
+/* bf16 variants: the same 0/1 observation values, half the bytes (optional format for GPU-resident training) */
+int mapf_observe_bf16(MapfEnv *e, uint16_t *obs_bf16, float *vec, void *stream) {
+    NEED_ENV("mapf_observe_bf16");
+    if (!obs_bf16 || !vec) return fail(MAPF_E_NULL, "mapf_observe_bf16: null argument");
+    CU(launch_observe(e->v, reinterpret_cast<float *>(obs_bf16), vec, e->d_work, (cudaStream_t)stream, 1));
+    return MAPF_OK;
+}
+
+int mapf_step_observe_bf16(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, uint16_t *obs_bf16, float *vec, void *stream) {
+    NEED_ENV("mapf_step_observe_bf16");
+    if (!actions || !out || !obs_bf16 || !vec) return fail(MAPF_E_NULL, "mapf_step_observe_bf16: null argument");
+    if (int rc = check_step_n(e, "mapf_step_observe_bf16")) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    float *obs = reinterpret_cast<float *>(obs_bf16);
+    if (step_observe_fusable(e->v) && !(e->v.dbg_flags & 1)) {
+        CU(launch_step_observe(e->v, actions, *out, obs, vec, e->d_work, s, 1));
+    } else {
+        CU(do_step(e, actions, nullptr, *out, MODE_FUSED, s));
+        CU(launch_observe(e->v, obs, vec, e->d_work, s, 1));
+    }
+    return MAPF_OK;
+}
+
 int mapf_bfs(MapfEnv *e, const int32_t *agent_list, int64_t n, int16_t *out, void *stream) {
     NEED_ENV("mapf_bfs");
     if (!out) return fail(MAPF_E_NULL, "mapf_bfs: null out");

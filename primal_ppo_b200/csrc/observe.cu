@@ -102,19 +102,21 @@ cudaError_t launch_t(const EnvView &v, float *obs, float *vec, const ObsLayout &
 
 }  // namespace
 
-cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t stream) {
+cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t stream, int out_bf16) {
     const int PB = v.C * v.F * v.F;
     // worlds whose block needs several warp passes: one CTA per world with shared staging (observe_wide.cu)
     if ((v.N > 32 || (size_t)v.N * ((PB + 31) / 32 + 2) * 4 * 2 > 24 * 1024 || (v.dbg_flags & 4)) && !(v.dbg_flags & 2)) {
-        const cudaError_t e = launch_observe_wide(v, obs, vec, work_counter, stream);
+        const cudaError_t e = launch_observe_wide(v, obs, vec, work_counter, stream, out_bf16);
         if (e != cudaErrorNotSupported) return e;
     }
     // chunk of agents handled per phase-1 pass: as many as fit ~24 KB of bit-string scratch per warp
     int CH = v.N < 32 ? v.N : 32;
     while (CH > 4 && (size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 24 * 1024) CH >>= 1;
-    const bool vec4 = ((size_t)v.N * PB) % 4 == 0 && (CH >= v.N || ((size_t)CH * PB) % 4 == 0) &&
+    const size_t al = out_bf16 ? 8 : 4;               // elements per 16-byte store
+    const bool vec4 = ((size_t)v.N * PB) % al == 0 && (CH >= v.N || ((size_t)CH * PB) % al == 0) &&
                       (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
-    const ObsLayout L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
+    ObsLayout L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
+    L.out_bf16 = out_bf16;
     int wpb = WARPS_PER_BLOCK;
     while (wpb > 1 && L.total * wpb > 200 * 1024) wpb >>= 1;
     if (L.total * wpb > 227 * 1024) return cudaErrorInvalidConfiguration;

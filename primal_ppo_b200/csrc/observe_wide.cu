@@ -92,7 +92,7 @@ observe_wide_kernel(const EnvView v, float *__restrict__ obs, float *__restrict_
 }  // namespace
 
 // Returns cudaErrorNotSupported when the shape is better served (or only served) by the warp-per-world kernel.
-cudaError_t launch_observe_wide(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t stream) {
+cudaError_t launch_observe_wide(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t stream, int out_bf16) {
     const int PB = v.C * v.F * v.F;
     // chunk size: per-warp scratch (aw + wb) of at most ~12 KB, and at least one chunk per warp when N allows it
     int CH = 32;
@@ -100,12 +100,14 @@ cudaError_t launch_observe_wide(const EnvView &v, float *obs, float *vec, int *w
     if ((size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 28 * 1024) return cudaErrorNotSupported;
     ObsLayout L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
     L.alias = 0;
+    L.out_bf16 = out_bf16;
     // the CTA-shared part: [obits | abits | grid | goals+cells]; make_layout put goals at off_goal (after the staging)
     const int shared_bytes = (int)(L.off_goal + (((size_t)v.N * 8 + 15) / 16) * 16);
     const int per_warp = (int)((((size_t)CH * L.AST * 4 + 15) / 16) * 16 + (((size_t)L.WB * 4 + 15) / 16) * 16);
     const size_t smem = (size_t)shared_bytes + (size_t)per_warp * WIDE_WARPS;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
-    const bool vec4 = ((size_t)CH * PB) % 4 == 0 && ((size_t)v.N * PB) % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+    const size_t al = out_bf16 ? 8 : 4;
+    const bool vec4 = ((size_t)CH * PB) % al == 0 && ((size_t)v.N * PB) % al == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -17,6 +17,7 @@ struct ObsLayout {
     int CH;      // agents per chunk (<= 32)
     int WB;      // u32 words of the chunk bit string
     int alias;   // 1: the chunk bit string overlays the staging area (single chunk per world)
+    int out_bf16; // 0: f32 observations (the reference's layout); 1: the same 0/1 values as bf16 (optional, half the bytes)
     int step_n, step_e;   // 1024 / PB, 1024 % PB: how (agent, bit) advances when the word index advances by 32
     size_t off_abits, off_grid, off_goal, off_aw, off_wb, total;
 };
@@ -30,6 +31,7 @@ inline ObsLayout make_layout(int HP, int RW, int GS, int N, int C, int F, int CH
     L.CH = CH;
     L.WB = (CH * L.PB + 31) / 32 + 2;
     L.alias = (CH >= N) ? 1 : 0;
+    L.out_bf16 = 0;
     L.step_n = 1024 / L.PB;
     L.step_e = 1024 % L.PB;
     size_t o = align16((size_t)HP * RW * 4);
@@ -219,6 +221,26 @@ __device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout 
         }
         __syncwarp();
         // ---- phase 2: bits -> floats, streaming stores ---------------------------------------------------------
+        if (L.out_bf16) {
+            // optional bf16 output: 8 bits -> 8 bf16 (1.0 = 0x3F80) -> one 16-byte store; the expansion is plain ALU
+            uint16_t *dst16 = reinterpret_cast<uint16_t *>(obs) + ((size_t)w * N + c0) * PB;
+            if (VEC4) {
+                const int n8 = TB >> 3;
+                for (int q = lane; q < n8; q += 32) {
+                    const uint32_t b = wb[q >> 2] >> ((q & 3) << 3);
+                    const uint32_t x0 = (b & 1u) * 0x3F80u | (b & 2u) * 0x1FC00000u;
+                    const uint32_t x1 = ((b >> 2) & 1u) * 0x3F80u | ((b >> 2) & 2u) * 0x1FC00000u;
+                    const uint32_t x2 = ((b >> 4) & 1u) * 0x3F80u | ((b >> 4) & 2u) * 0x1FC00000u;
+                    const uint32_t x3 = ((b >> 6) & 1u) * 0x3F80u | ((b >> 6) & 2u) * 0x1FC00000u;
+                    st_stream_v4(reinterpret_cast<float *>(dst16 + ((size_t)q << 3)), x0, x1, x2, x3);
+                }
+                for (int f = (n8 << 3) + lane; f < TB; f += 32) dst16[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 0x3F80 : 0;
+            } else {
+                for (int f = lane; f < TB; f += 32) dst16[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 0x3F80 : 0;
+            }
+            __syncwarp();
+            return;
+        }
         float *dst = obs + ((size_t)w * N + c0) * PB;
         if (VEC4) {
             const int n4 = TB >> 2;

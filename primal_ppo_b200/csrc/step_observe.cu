@@ -134,11 +134,12 @@ bool step_observe_fusable(const EnvView &v) {
 }
 
 cudaError_t launch_step_observe(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
-                                int *work_counter, cudaStream_t stream) {
+                                int *work_counter, cudaStream_t stream, int out_bf16) {
     const int PB = v.C * v.F * v.F;
     const int CH = obs_chunk(v);
-    const bool vec4 = ((size_t)v.N * PB) % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
-    const ObsLayout L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
+    const bool vec4 = ((size_t)v.N * PB) % (out_bf16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+    ObsLayout L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
+    L.out_bf16 = out_bf16;
     if (v.C == 6 && v.F == 9) {
         return vec4 ? launch_t<6, 9, true>(v, actions, out, obs, vec, L, work_counter, stream)
                     : launch_t<6, 9, false>(v, actions, out, obs, vec, L, work_counter, stream);

@@ -184,8 +184,8 @@ class BatchedMapfGym:
         o = self._out if out is None else out
         obs, vec = self._obs_buffers(obs_out)
         so = self._step_out(o)
-        _cabi.check(self._lib.mapf_step_observe(self._h, _ptr(a), C.byref(so), _ptr(obs), _ptr(vec), self._stream()),
-                    "mapf_step_observe")
+        fn = self._lib.mapf_step_observe_bf16 if obs.dtype == torch.bfloat16 else self._lib.mapf_step_observe
+        _cabi.check(fn(self._h, _ptr(a), C.byref(so), _ptr(obs), _ptr(vec), self._stream()), "mapf_step_observe")
         self._eval_key = None
         return o, obs, vec
 
@@ -197,7 +197,8 @@ class BatchedMapfGym:
                 self._vec = torch.empty((self.W, self.N, 4), dtype=torch.float32, device=self.device)
             return self._obs, self._vec
         obs, vec = out
-        assert obs.is_contiguous() and vec.is_contiguous() and obs.dtype == torch.float32 and vec.dtype == torch.float32
+        assert obs.is_contiguous() and vec.is_contiguous() and vec.dtype == torch.float32
+        assert obs.dtype in (torch.float32, torch.bfloat16), "observations are f32 (reference layout) or, optionally, bf16"
         assert obs.numel() == self.W * self.N * self.C * self.F * self.F and vec.numel() == self.W * self.N * 4
         return obs, vec
 
@@ -205,7 +206,8 @@ class BatchedMapfGym:
         """``getAllObservations`` (mapf_gym.py:327-336).  ``out=(obs, vec)`` writes straight into the policy's input
         tensors; otherwise env-owned tensors are (re)used."""
         obs, vec = self._obs_buffers(out)
-        _cabi.check(self._lib.mapf_observe(self._h, _ptr(obs), _ptr(vec), self._stream()), "mapf_observe")
+        fn = self._lib.mapf_observe_bf16 if obs.dtype == torch.bfloat16 else self._lib.mapf_observe
+        _cabi.check(fn(self._h, _ptr(obs), _ptr(vec), self._stream()), "mapf_observe")
         return obs, vec
 
     # ---- BFS distance-to-goal maps (agent.bfsMap, mapf_gym.py:211-244) -------------------------------------------

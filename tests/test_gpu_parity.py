@@ -225,6 +225,26 @@ def test_gpu_maximum_sizes_and_empty_inputs():
         env.step(torch.zeros((3, 254), dtype=torch.int8))                  # wrong shape (mapf_gym.py:437 assert)
 
 
+@pytest.mark.parametrize("shape", [(512, 40, 40, 32, 9), (33, 20, 20, 8, 9), (7, 12, 9, 5, 9), (6, 64, 64, 31, 15),
+                                   (4, 80, 80, 128, 21), (3, 9, 9, 3, 3)])
+def test_gpu_bf16_observations_equal_f32(shape):
+    """Optional bf16 output format: the same 0/1 values (exact in bf16), from both the stand-alone and the fused launch."""
+    W, H, Wd, N, F = shape
+    sc = random_scenario(W, H, Wd, N, density=(0.0, 0.3), queue_len=3, seed=W + F, fov=F, unique_maps=min(W, 32))
+    e1, e2 = _env(sc, use_tape=False), _env(sc, use_tape=False)
+    a = torch.from_numpy(random_actions(4, W, N, seed=1)).cuda()
+    ob16 = torch.empty((W, N, 6, F, F), dtype=torch.bfloat16, device="cuda")
+    v16 = torch.empty((W, N, 4), device="cuda")
+    obs, vec = e1.getAllObservations()
+    e2.getAllObservations(out=(ob16, v16))
+    assert torch.equal(ob16.float(), obs) and torch.equal(v16, vec)
+    for t in range(4):
+        o1, obs, vec = e1.step_observe(a[t])
+        o2, _, _ = e2.step_observe(a[t], obs_out=(ob16, v16))
+        assert torch.equal(ob16.float(), obs) and torch.equal(v16, vec), (shape, t)
+        assert torch.equal(o1.reward, o2.reward) and torch.equal(o1.status, o2.status)
+
+
 def test_gpu_sharded_worlds_equal_unsharded():
     """World w gives the same bits whichever rank owns it: run worlds [0,W) in one env and as two shards
     (world_offset keys the Philox draws), compare every output."""
