@@ -97,9 +97,9 @@ class RolloutBuffer:
     cost_returns: Optional[torch.Tensor] = None
 
     @staticmethod
-    def allocate(T, W, N, C, F, device):
-        f32, z = torch.float32, lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=device)
-        return RolloutBuffer(obs=z(T + 1, W, N, C, F, F), vec=z(T + 1, W, N, 4), actions=z(T, W, N, dt=torch.int8),
+    def allocate(T, W, N, C, F, device, obs_dtype=torch.float32):
+        z = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=device)
+        return RolloutBuffer(obs=z(T + 1, W, N, C, F, F, dt=obs_dtype), vec=z(T + 1, W, N, 4), actions=z(T, W, N, dt=torch.int8),
                              ps=z(T, W, N, 5), values=z(T, W, N), cost_values=z(T, W, N), rewards=z(T, W, N),
                              cost_rewards=z(T, W, N), train_valid=z(T, W, N, 5), status=z(T, W, N, dt=torch.int8),
                              goals_reached=z(T, W, N, dt=torch.uint8), violated=z(T, W, N, dt=torch.uint8),
@@ -123,7 +123,12 @@ class VecPPOTrainer:
     MINIBATCH_SIZE = 256 rows of one env (`driver.py:121-131`; its index set only ever covers the first env's rows)."""
 
     def __init__(self, env, policy: ScrimpPolicy, cfg: PPOConfig = PPOConfig(), group=None, amp_dtype=None,
-                 rows_per_minibatch: Optional[int] = None, forward_chunk_rows: int = 1 << 15, seed: int = 1234):
+                 rows_per_minibatch: Optional[int] = None, forward_chunk_rows: int = 1 << 15, seed: int = 1234,
+                 obs_dtype=torch.float32):
+        """obs_dtype=torch.bfloat16 stores the rollout's observations in the env's optional bf16 format (same values, half
+        the memory and half the env's store traffic); it needs amp_dtype=torch.bfloat16."""
+        if obs_dtype == torch.bfloat16 and amp_dtype != torch.bfloat16:
+            raise ValueError("bf16 observations need amp_dtype=torch.bfloat16 (the fp32 convolution would reject them)")
         self.env, self.policy, self.cfg, self.group = env, policy, cfg, group
         self.learner = PPOLearner(policy, cfg, group, amp_dtype)
         self.amp_dtype = amp_dtype
@@ -131,7 +136,7 @@ class VecPPOTrainer:
         self.rows_per_minibatch = rows_per_minibatch or cfg.minibatch_size
         self.chunk = forward_chunk_rows
         self.seed, self.sample_calls = seed, 0
-        self.buf = RolloutBuffer.allocate(self.T, env.W, env.N, env.C, env.F, env.device)
+        self.buf = RolloutBuffer.allocate(self.T, env.W, env.N, env.C, env.F, env.device, obs_dtype)
         self.gen = torch.Generator(device=env.device); self.gen.manual_seed(seed)
         env.getAllObservations(out=(self.buf.obs[0], self.buf.vec[0]))
 

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--rows", type=int, default=256, help="(time, world) rows per minibatch per GPU")
     ap.add_argument("--minibatches", type=int, default=8)
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--bf16-obs", action="store_true", help="rollout observations in the env's optional bf16 format")
     args = ap.parse_args()
     from primal_ppo_b200 import BatchedMapfGym, random_scenario
     from primal_ppo_b200.build import build
@@ -49,7 +50,8 @@ def main():
     pol = ScrimpPolicy().to(dev).use_channels_last()
     cfg = PPOConfig(n_steps=T, n_epochs=1)
     amp = None if args.fp32 else torch.bfloat16
-    tr = VecPPOTrainer(env, pol, cfg, group=group, amp_dtype=amp, rows_per_minibatch=args.rows, seed=1234 + rank)
+    tr = VecPPOTrainer(env, pol, cfg, group=group, amp_dtype=amp, rows_per_minibatch=args.rows, seed=1234 + rank,
+                       obs_dtype=torch.bfloat16 if args.bf16_obs else torch.float32)
 
     def sync():
         if ws > 1:
