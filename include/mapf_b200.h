@@ -157,6 +157,15 @@ int mapf_sample_actions(const float *ps, int64_t rows, uint64_t seed, uint32_t d
  * pos/goal int16 [W,N,2], rep int8 [W,N] (the repetition action or -1, mapf_gym.py:161), err u32 [W]. */
 int mapf_get_state(MapfEnv *env, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream);
 
+/* Checkpoint / resume of everything reset and step mutate (cells, goals, repetition actions, queue cursors, human tick,
+ * tape cursor, step count, error flags, episode counters) as one opaque device blob of mapf_state_bytes() bytes.  The
+ * scenario arrays are not part of it (they are borrowed and immutable): a blob is valid for an env created with the same
+ * MapfConfig and reset with the same scenario.  The reference has no counterpart (its envs are rebuilt every rollout,
+ * runner.py:30). */
+int64_t mapf_state_bytes(MapfEnv *env);
+int mapf_save_state(MapfEnv *env, void *blob, void *stream);
+int mapf_load_state(MapfEnv *env, const void *blob, void *stream);
+
 /* Episode counters accumulated on device (util.py:56-65 OneEpPerformance, filled in runner.py:66-99):
  * int64 [W,6] = totalGoals, shadowGoals, staticCollide, humanCollide, agentCollide, constraintViolations. */
 int mapf_get_counters(MapfEnv *env, int64_t *counters, void *stream);

@@ -14,7 +14,7 @@ EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy"
             "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae",
             "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe",
             "mapf_sample_actions", "mapf_generate_scenario",
-            "mapf_observe_bf16", "mapf_step_observe_bf16"]
+            "mapf_observe_bf16", "mapf_step_observe_bf16", "mapf_state_bytes", "mapf_save_state", "mapf_load_state"]
 
 ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE = 1, 2, 4, 8
 
@@ -81,12 +81,16 @@ def load_library():
     lib.mapf_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp, vp, vp]
     lib.mapf_sample_actions.argtypes = [vp, i64, C.c_uint64, C.c_uint32, vp, vp, vp]
     lib.mapf_generate_scenario.argtypes = [C.POINTER(MapfGenConfig)] + [vp] * 9
+    lib.mapf_state_bytes.argtypes = [vp]
+    lib.mapf_save_state.argtypes = [vp, vp, vp]
+    lib.mapf_load_state.argtypes = [vp, vp, vp]
     lib.mapf_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.mapf_get_counters.argtypes = [vp, vp, vp]
     lib.mapf_step_observe_host.argtypes = [vp, vp, C.POINTER(MapfStepOutHost), vp, vp, vp, vp, vp, vp]
     for n in EXPORTED:
         if n not in ("mapf_last_error",):
             getattr(lib, n).restype = C.c_int
+    lib.mapf_state_bytes.restype = C.c_int64
     lib.mapf_last_error.restype = C.c_char_p
     _lib = lib
     return lib

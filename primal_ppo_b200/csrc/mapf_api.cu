@@ -337,6 +337,56 @@ int mapf_get_state(MapfEnv *e, int16_t *pos, int16_t *goal, int8_t *rep, uint32_
     return MAPF_OK;
 }
 
+// ---- checkpoint / resume of the env's mutable state ------------------------------------------------------------------
+namespace {
+struct StatePiece { void *p; size_t bytes; };
+// every buffer step / reset mutate, in a fixed order; sizes are rounded up to 16 bytes inside the blob
+int state_pieces(MapfEnv *e, StatePiece *out) {
+    EnvView &v = e->v;
+    const size_t W = v.W, WN = (size_t)v.W * v.N;
+    int n = 0;
+    out[n++] = {v.pos, WN * 4}; out[n++] = {v.goal, WN * 4}; out[n++] = {v.rep, WN}; out[n++] = {v.qcur, WN * 4};
+    out[n++] = {v.htick, W * 4}; out[n++] = {v.tape_cur, W * 4}; out[n++] = {v.nstep, W * 4}; out[n++] = {v.err, W * 4};
+    out[n++] = {v.counters, W * 48}; out[n++] = {v.hcur, W * 8}; out[n++] = {v.hnx, W * 8};
+    return n;
+}
+}  // namespace
+
+int64_t mapf_state_bytes(MapfEnv *e) {
+    if (!e) return fail(MAPF_E_NULL, "mapf_state_bytes: null env");
+    StatePiece pc[16];
+    const int n = state_pieces(e, pc);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += (pc[i].bytes + 15) & ~(size_t)15;
+    return (int64_t)total;
+}
+
+int mapf_save_state(MapfEnv *e, void *blob, void *stream) {
+    NEED_ENV("mapf_save_state");
+    if (!blob) return fail(MAPF_E_NULL, "mapf_save_state: null blob");
+    StatePiece pc[16];
+    const int n = state_pieces(e, pc);
+    char *dst = static_cast<char *>(blob);
+    for (int i = 0; i < n; ++i) {
+        CU(cudaMemcpyAsync(dst, pc[i].p, pc[i].bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        dst += (pc[i].bytes + 15) & ~(size_t)15;
+    }
+    return MAPF_OK;
+}
+
+int mapf_load_state(MapfEnv *e, const void *blob, void *stream) {
+    NEED_ENV("mapf_load_state");
+    if (!blob) return fail(MAPF_E_NULL, "mapf_load_state: null blob");
+    StatePiece pc[16];
+    const int n = state_pieces(e, pc);
+    const char *src = static_cast<const char *>(blob);
+    for (int i = 0; i < n; ++i) {
+        CU(cudaMemcpyAsync(pc[i].p, src, pc[i].bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        src += (pc[i].bytes + 15) & ~(size_t)15;
+    }
+    return MAPF_OK;
+}
+
 int mapf_get_counters(MapfEnv *e, int64_t *counters, void *stream) {
     if (!e || !counters) return fail(MAPF_E_NULL, "mapf_get_counters: null argument");
     CU(cudaMemcpyAsync(counters, e->v.counters, (size_t)e->v.W * 6 * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

@@ -245,6 +245,20 @@ class BatchedMapfGym:
                     "mapf_get_state")
         return dict(pos=pos, goal=goal, rep=rep, err=err)
 
+    def save_state(self) -> torch.Tensor:
+        """Checkpoint of the env's mutable state as an opaque uint8 device tensor (``load_state`` restores it)."""
+        n = int(self._lib.mapf_state_bytes(self._h))
+        if n < 0:
+            _cabi.check(n, "mapf_state_bytes")
+        blob = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        _cabi.check(self._lib.mapf_save_state(self._h, _ptr(blob), self._stream()), "mapf_save_state")
+        return blob
+
+    def load_state(self, blob: torch.Tensor) -> None:
+        assert blob.dtype == torch.uint8 and blob.is_contiguous() and blob.numel() == int(self._lib.mapf_state_bytes(self._h))
+        _cabi.check(self._lib.mapf_load_state(self._h, _ptr(blob.to(self.device)), self._stream()), "mapf_load_state")
+        self._eval_key = None
+
     def counters(self):
         """OneEpPerformance counters per world (util.py:56-65): int64 [W,6] =
         totalGoals, shadowGoals, staticCollide, humanCollide, agentCollide, constraintViolations."""
