@@ -67,6 +67,23 @@ class PPOLearner:
         stats["lagrangian"] = self.lagrange.value()
         return stats
 
+    # ---- checkpoints in the reference's layout (driver.py:164-208) ---------------------------------------------------
+    def save_checkpoint(self, path: str, step: int = 0, episode: int = 0, reward: float = 0.0) -> None:
+        """`net_checkpoint.pkl`: {"model", "optimizer", "step", "episode", "reward"} with "model" keyed like the
+        reference's SCRIMPNet, so the reference's `evaluate.py` / `RETRAIN` path can load it; "lagrange" is an extra key."""
+        torch.save({"model": self.policy.reference_state_dict(), "optimizer": self.opt.state_dict(), "step": int(step),
+                    "episode": int(episode), "reward": float(reward), "lagrange": self.lagrange.state_dict()}, path)
+
+    def load_checkpoint(self, path: str, load_optimizer: bool = True) -> dict:
+        """Loads a checkpoint written by `save_checkpoint` OR by the reference (`driver.py:189-194`).  The reference's Adam
+        state is indexed by ITS parameter order and is therefore only restored from checkpoints written here."""
+        ck = torch.load(path, map_location=self.flat_grad.device, weights_only=False)
+        self.policy.load_reference_state_dict(ck["model"])
+        if load_optimizer and "lagrange" in ck:
+            self.opt.load_state_dict(ck["optimizer"])
+            self.lagrange.load_state_dict(ck["lagrange"])
+        return {k: ck[k] for k in ("step", "episode", "reward") if k in ck}
+
     def state_dict(self):
         return {"model": self.policy.state_dict(), "optimizer": self.opt.state_dict(),
                 "lagrange": self.lagrange.state_dict()}
