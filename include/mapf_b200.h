@@ -115,7 +115,8 @@ int mapf_joint_step(MapfEnv *env, const int8_t *actions, const int8_t *status, u
  * (runner.py:89-91). */
 int mapf_step(MapfEnv *env, const int8_t *actions, const MapfStepOut *out, void *stream);
 
-/* getAllObservations (mapf_gym.py:327-336): obs f32 [W,N,C,F,F], vec f32 [W,N,4], written in place. */
+/* getAllObservations (mapf_gym.py:327-336): obs f32 [W,N,C,F,F], vec f32 [W,N,4], written in place.  vec must be
+ * 16-byte aligned (one store per agent); obs may have any 4-byte alignment (16-byte aligned buffers take the fast path). */
 int mapf_observe(MapfEnv *env, float *obs, float *vec, void *stream);
 
 /* One env step of the rollout loop in ONE launch (runner.py:64-100): mapf_step followed by mapf_observe of the new

@@ -184,6 +184,11 @@ int mapf_reset(MapfEnv *e, const MapfScenario *sc, void *stream) {
     if (!e) return fail(MAPF_E_NULL, name ": null env");                                   \
     if (!e->has_scenario) return fail(MAPF_E_STATE, name ": mapf_reset has not been called")
 
+// vec is written with one 16-byte store per agent
+static int check_vec(const float *vec, const char *name) {
+    if (reinterpret_cast<uintptr_t>(vec) & 15) return fail(MAPF_E_BAD_CONFIG, "%s: vec must be 16-byte aligned", name);
+    return MAPF_OK;
+}
 static int check_step_n(const MapfEnv *e, const char *name) {
     if (e->v.N > 128) return fail(MAPF_E_UNSUPPORTED, "%s: joint-step resolution supports N <= 128 agents per world (got %d)", name, e->v.N);
     return MAPF_OK;
@@ -224,6 +229,7 @@ int mapf_step(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, void *s
 
 int mapf_observe(MapfEnv *e, float *obs, float *vec, void *stream) {
     NEED_ENV("mapf_observe");
+    if (int rc = check_vec(vec, "mapf_observe")) return rc;
     if (!obs || !vec) return fail(MAPF_E_NULL, "mapf_observe: null argument");
     CU(launch_observe(e->v, obs, vec, e->d_work, (cudaStream_t)stream));
     return MAPF_OK;
@@ -231,6 +237,7 @@ int mapf_observe(MapfEnv *e, float *obs, float *vec, void *stream) {
 
 int mapf_step_observe(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, float *obs, float *vec, void *stream) {
     NEED_ENV("mapf_step_observe");
+    if (int rc = check_vec(vec, "mapf_step_observe")) return rc;
     if (!actions || !out || !obs || !vec) return fail(MAPF_E_NULL, "mapf_step_observe: null argument");
     if (int rc = check_step_n(e, "mapf_step_observe")) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -246,6 +253,7 @@ int mapf_step_observe(MapfEnv *e, const int8_t *actions, const MapfStepOut *out,
 /* bf16 variants: the same 0/1 observation values, half the bytes (optional format for GPU-resident training) */
 int mapf_observe_bf16(MapfEnv *e, uint16_t *obs_bf16, float *vec, void *stream) {
     NEED_ENV("mapf_observe_bf16");
+    if (int rc = check_vec(vec, "mapf_observe_bf16")) return rc;
     if (!obs_bf16 || !vec) return fail(MAPF_E_NULL, "mapf_observe_bf16: null argument");
     CU(launch_observe(e->v, reinterpret_cast<float *>(obs_bf16), vec, e->d_work, (cudaStream_t)stream, 1));
     return MAPF_OK;
@@ -253,6 +261,7 @@ int mapf_observe_bf16(MapfEnv *e, uint16_t *obs_bf16, float *vec, void *stream) 
 
 int mapf_step_observe_bf16(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, uint16_t *obs_bf16, float *vec, void *stream) {
     NEED_ENV("mapf_step_observe_bf16");
+    if (int rc = check_vec(vec, "mapf_step_observe_bf16")) return rc;
     if (!actions || !out || !obs_bf16 || !vec) return fail(MAPF_E_NULL, "mapf_step_observe_bf16: null argument");
     if (int rc = check_step_n(e, "mapf_step_observe_bf16")) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -396,6 +405,7 @@ int mapf_get_counters(MapfEnv *e, int64_t *counters, void *stream) {
 int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfStepOutHost *out, float *obs_dev,
                            float *vec_dev, float *train_valid_dev, float *obs_host, float *vec_host, void *stream) {
     NEED_ENV("mapf_step_observe_host");
+    if (int rc = check_vec(vec_dev, "mapf_step_observe_host")) return rc;
     if (!actions_host || !out || !obs_dev || !vec_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host: null argument");
     if (int rc = check_step_n(e, "mapf_step_observe_host")) return rc;
     const EnvView &v = e->v;

@@ -274,6 +274,35 @@ def test_gpu_checkpoint_resume_reproduces_the_rollout():
             assert torch.equal(x, y) and torch.equal(x, z)
 
 
+def test_gpu_unaligned_output_buffers():
+    """Outputs that are not 16-byte aligned take the scalar-store paths (obs f32 / bf16, BFS tiles) and give the same
+    bits; a misaligned vec is refused."""
+    from primal_ppo_b200._cabi import MapfError
+    sc = random_scenario(37, 20, 20, 8, density=(0.1, 0.25), queue_len=3, seed=5, unique_maps=16)
+    env = _env(sc, use_tape=False)
+    a = torch.from_numpy(random_actions(3, 37, 8, seed=2)).cuda()
+    n = 37 * 8 * 6 * 81
+    big = torch.zeros(n + 8, device="cuda")
+    big16 = torch.zeros(n + 8, dtype=torch.bfloat16, device="cuda")
+    vec = torch.empty((37, 8, 4), device="cuda")
+    for t in range(3):
+        _, obs, v = env.step_observe(a[t])
+        o1 = big[1:1 + n].view(37, 8, 6, 9, 9)                     # 4-byte aligned only
+        env.getAllObservations(out=(o1, vec))
+        assert torch.equal(o1, obs) and torch.equal(vec, v) and float(big[0]) == 0 and float(big[1 + n]) == 0
+        o2 = big16[1:1 + n].view(37, 8, 6, 9, 9)                   # 2-byte aligned only
+        env.getAllObservations(out=(o2, vec))
+        assert torch.equal(o2.float(), obs) and float(big16[0]) == 0 and float(big16[1 + n]) == 0
+    ref = env.bfs_maps()
+    raw = torch.zeros(ref.numel() + 4, dtype=torch.int16, device="cuda")
+    out = raw[1:1 + ref.numel()].view(ref.shape)
+    env.bfs_maps(out=out)
+    assert torch.equal(out, ref) and int(raw[0]) == 0 and int(raw[-1]) == 0
+    vraw = torch.zeros(37 * 8 * 4 + 4, device="cuda")
+    with pytest.raises(MapfError):
+        env.getAllObservations(out=(big[0:n].view(37, 8, 6, 9, 9), vraw[1:1 + 37 * 8 * 4].view(37, 8, 4)))
+
+
 def test_gpu_sharded_worlds_equal_unsharded():
     """World w gives the same bits whichever rank owns it: run worlds [0,W) in one env and as two shards
     (world_offset keys the Philox draws), compare every output."""
