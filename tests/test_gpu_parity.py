@@ -372,6 +372,30 @@ def test_gpu_gae_bit_exact():
         _eq(_np(adv), radv, f"gae adv {T}x{cols}")
 
 
+def test_gpu_gae_with_terminal_mask():
+    """nonterminal[t] = 0 cuts the bootstrap and the advantage carry at step t (the reference always uses 1.0,
+    runner.py:123; the mask is the generalisation to episodic envs).  NumPy f32 restatement, op by op."""
+    from primal_ppo_b200 import gae
+    rng = np.random.default_rng(9)
+    T, cols = 37, 203
+    r = rng.normal(size=(T, cols)).astype(np.float32); v = rng.normal(size=(T, cols)).astype(np.float32)
+    lv = rng.normal(size=(cols,)).astype(np.float32)
+    nt = (rng.random((T, cols)) > 0.1).astype(np.uint8)
+    g, gl = np.float32(0.95), np.float32(0.95 * 0.95)
+    ret = np.zeros_like(r); adv = np.zeros_like(r)
+    last = np.zeros(cols, dtype=np.float32); nv = lv.copy()
+    for t in range(T - 1, -1, -1):
+        m = nt[t].astype(bool)
+        m1 = np.where(m, g * nv, np.float32(0)).astype(np.float32)
+        delta = ((r[t] + m1).astype(np.float32) - v[t]).astype(np.float32)
+        m2 = np.where(m, gl * last, np.float32(0)).astype(np.float32)
+        last = (delta + m2).astype(np.float32)
+        adv[t] = last; ret[t] = (last + v[t]).astype(np.float32); nv = v[t]
+    out, a = gae(torch.from_numpy(r).cuda(), torch.from_numpy(v).cuda(), torch.from_numpy(lv).cuda(),
+                 nonterminal=torch.from_numpy(nt).cuda(), return_advantages=True)
+    _eq(_np(out), ret, "masked returns"); _eq(_np(a), adv, "masked advantages")
+
+
 def test_gpu_host_buffer_call_equals_device_call():
     sc = random_scenario(512, 20, 20, 8, density=(0.1, 0.2), queue_len=4, seed=31, unique_maps=64)
     a = random_actions(6, 512, 8, seed=3)
