@@ -10,7 +10,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libmapf_b200.so")
 SOURCES = ["mapf_api.cu", "step.cu", "step_wide.cu", "observe.cu", "observe_wide.cu", "step_observe.cu", "bfs.cu", "gae.cu", "glue.cu", "scenario_gen.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
-              "-Xcompiler", "-fPIC,-fvisibility=default", "-shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC,-fvisibility=default", "-shared", "-cudart", "shared", "--threads", "0"]
 
 
 def _stale() -> bool:
