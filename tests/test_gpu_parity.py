@@ -322,6 +322,37 @@ def test_gpu_sharded_worlds_equal_unsharded():
     assert torch.equal(full.state()["err"], torch.cat([lo.state()["err"], hi.state()["err"]]))
 
 
+def test_gpu_bfs_deep_mazes():
+    """Serpentine corridors next to ordinary maps in one batch: distances of several hundred (far beyond a byte), and
+    warps whose maps finish after very different numbers of levels."""
+    from primal_ppo_b200.scenario import Scenario, looping_trace
+    W, H, N = 12, 40, 6
+    base = random_scenario(W, H, H, N, density=(0.0, 0.2), queue_len=3, seed=4)
+    obst = base.obst.copy()
+    for w in range(0, W, 2):                                  # every other world becomes a serpentine maze
+        m = np.zeros((H, H), dtype=np.uint8)
+        for r in range(1, H, 2):
+            m[r, :] = 1
+            m[r, H - 1 if (r // 2) % 2 == 0 else 0] = 0
+        obst[w] = m
+    starts = base.starts.copy(); queue = base.goal_queue.copy(); htrace = base.htrace.copy(); hlen = base.hlen.copy()
+    for w in range(0, W, 2):                                  # agents, goals and the human on open rows of the maze
+        for i in range(N):
+            starts[w, i] = (2 * i, 3 + i)
+            queue[w, i, :] = (38 - 2 * i, 5 + i)
+        tr = looping_trace([(0, 0), (0, 1), (0, 0)])
+        htrace[w, :3] = tr; htrace[w, 3:] = tr[-1]; hlen[w] = 3
+    sc = Scenario(obst=obst, starts=starts, goal_queue=queue, htrace=htrace, hlen=hlen)
+    sc.validate()
+    orc = OracleMapfGym(sc, threads=4, use_tape=False)
+    env = _env(sc, use_tape=False)
+    ref = orc.bfs_maps()
+    assert ref[0].max() > 600 and ref[1].max() < 200
+    _eq(_np(env.bfs_maps()), ref, "deep + shallow maps")
+    ids = torch.tensor([0, 7, 13, 2 * N + 1, 5], dtype=torch.int32).cuda()
+    _eq(_np(env.bfs_maps(agent_ids=ids)), ref.reshape(W * N, H, H)[ids.cpu().numpy()], "listed maps")
+
+
 def test_gpu_bfs_refresh_in_place():
     sc = random_scenario(256, 40, 40, 32, density=(0.0, 0.3), queue_len=8, seed=21, unique_maps=32)
     orc = OracleMapfGym(sc, threads=8, use_tape=False)
