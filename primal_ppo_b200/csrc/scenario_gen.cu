@@ -56,6 +56,7 @@ struct GenSmem {
     uint8_t *freec;     // [H*Wd]
     uint8_t *occ;       // [H*Wd]
     int16_t *dist;      // [H*Wd]
+    uint32_t *fw, *nf;  // [ceil(H*Wd/32)] frontier bit sets of the current / next BFS level
 };
 
 __global__ void __launch_bounds__(128) scenario_gen_kernel(const GenView g, const int per_warp) {
@@ -69,6 +70,9 @@ __global__ void __launch_bounds__(128) scenario_gen_kernel(const GenView g, cons
     s.freec = base;
     s.occ = base + ((cells + 15) & ~15);
     s.dist = reinterpret_cast<int16_t *>(base + 2 * ((cells + 15) & ~15));
+    const int fwords = (cells + 31) / 32;
+    s.fw = reinterpret_cast<uint32_t *>(base + 2 * ((cells + 15) & ~15) + ((cells * 2 + 15) & ~15));
+    s.nf = s.fw + ((fwords + 3) & ~3);
     const uint32_t gw = (uint32_t)(w + g.world_offset);
     uint32_t err = 0;
 
@@ -173,23 +177,30 @@ __global__ void __launch_bounds__(128) scenario_gen_kernel(const GenView g, cons
         for (int attempt = 0; attempt < 4 && d < 0; ++attempt) {
             goal = draw_cell(S_HUMAN, 2 + (uint32_t)loop * 8 + attempt, false);
             if (goal < 0 || goal == cur) { goal = -1; continue; }
-            // BFS distance field from the goal (level-synchronous over the warp)
+            // BFS distance field from the goal: level-synchronous, the frontier kept as a bit set so that a level
+            // costs work proportional to the frontier, not to the grid
             for (int c = lane; c < cells; c += 32) s.dist[c] = -1;
+            for (int k = lane; k < fwords; k += 32) { s.fw[k] = 0; s.nf[k] = 0; }
             __syncwarp();
-            if (lane == 0) s.dist[goal] = 0;
+            if (lane == 0) { s.dist[goal] = 0; s.fw[goal >> 5] = 1u << (goal & 31); }
             __syncwarp();
             for (int level = 0; level < cells; ++level) {
                 bool grew = false;
-                for (int c = lane; c < cells; c += 32) {
-                    if (s.dist[c] != level) continue;
-                    const int y = c / Wd, x = c - y * Wd;
-                    if (x + 1 < cols && s.freec[c + 1] && s.dist[c + 1] < 0) { s.dist[c + 1] = (int16_t)(level + 1); grew = true; }
-                    if (y + 1 < rows && s.freec[c + Wd] && s.dist[c + Wd] < 0) { s.dist[c + Wd] = (int16_t)(level + 1); grew = true; }
-                    if (x > 0 && s.freec[c - 1] && s.dist[c - 1] < 0) { s.dist[c - 1] = (int16_t)(level + 1); grew = true; }
-                    if (y > 0 && s.freec[c - Wd] && s.dist[c - Wd] < 0) { s.dist[c - Wd] = (int16_t)(level + 1); grew = true; }
+                for (int k = lane; k < fwords; k += 32) {
+                    uint32_t b = s.fw[k];
+                    while (b) {
+                        const int c = 32 * k + __ffs(b) - 1; b &= b - 1;
+                        const int y = c / Wd, x = c - y * Wd;
+                        // several frontier cells may claim the same neighbour: they all write the same level
+                        if (x + 1 < cols && s.freec[c + 1] && s.dist[c + 1] < 0) { s.dist[c + 1] = (int16_t)(level + 1); atomicOr(&s.nf[(c + 1) >> 5], 1u << ((c + 1) & 31)); grew = true; }
+                        if (y + 1 < rows && s.freec[c + Wd] && s.dist[c + Wd] < 0) { s.dist[c + Wd] = (int16_t)(level + 1); atomicOr(&s.nf[(c + Wd) >> 5], 1u << ((c + Wd) & 31)); grew = true; }
+                        if (x > 0 && s.freec[c - 1] && s.dist[c - 1] < 0) { s.dist[c - 1] = (int16_t)(level + 1); atomicOr(&s.nf[(c - 1) >> 5], 1u << ((c - 1) & 31)); grew = true; }
+                        if (y > 0 && s.freec[c - Wd] && s.dist[c - Wd] < 0) { s.dist[c - Wd] = (int16_t)(level + 1); atomicOr(&s.nf[(c - Wd) >> 5], 1u << ((c - Wd) & 31)); grew = true; }
+                    }
                 }
                 __syncwarp();
                 if (!__any_sync(FULL, grew) || s.dist[cur] >= 0) break;
+                for (int k = lane; k < fwords; k += 32) { s.fw[k] = s.nf[k]; s.nf[k] = 0; }
                 __syncwarp();
             }
             __syncwarp();
@@ -298,7 +309,8 @@ cudaError_t launch_scenario_gen(const MapfGenConfig &c, uint8_t *obst, int16_t *
     g.obst = obst; g.dims = dims; g.starts = starts; g.goal_queue = goal_queue; g.htrace = htrace; g.hp5 = hp5;
     g.hlen = hlen; g.gen_err = gen_err;
     const int cells = c.height * c.width;
-    const int per_warp = 2 * ((cells + 15) & ~15) + ((cells * 2 + 15) & ~15);
+    const int fwords = (cells + 31) / 32;
+    const int per_warp = 2 * ((cells + 15) & ~15) + ((cells * 2 + 15) & ~15) + 2 * ((fwords + 3) & ~3) * 4;
     int wpb = 4;
     while (wpb > 1 && per_warp * wpb > 160 * 1024) wpb >>= 1;
     const size_t smem = (size_t)per_warp * wpb;
