@@ -141,8 +141,10 @@ class VecPPOTrainer:
 
     def __init__(self, env, policy: ScrimpPolicy, cfg: PPOConfig = PPOConfig(), group=None, amp_dtype=None,
                  rows_per_minibatch: Optional[int] = None, forward_chunk_rows: int = 1 << 15, seed: int = 1234,
-                 obs_dtype=torch.float32):
-        """obs_dtype=torch.bfloat16 stores the rollout's observations in the env's optional bf16 format (same values, half
+                 obs_dtype=torch.float32, fresh_worlds=None):
+        """fresh_worlds: callable(rollout_index) -> scenario with the env's shapes; when given, every rollout starts on
+        new worlds, as the reference does (`env = MapfGym()` in `Runner.run`, runner.py:30).
+        obs_dtype=torch.bfloat16 stores the rollout's observations in the env's optional bf16 format (same values, half
         the memory and half the env's store traffic); it needs amp_dtype=torch.bfloat16."""
         if obs_dtype == torch.bfloat16 and amp_dtype != torch.bfloat16:
             raise ValueError("bf16 observations need amp_dtype=torch.bfloat16 (the fp32 convolution would reject them)")
@@ -153,6 +155,7 @@ class VecPPOTrainer:
         self.rows_per_minibatch = rows_per_minibatch or cfg.minibatch_size
         self.chunk = forward_chunk_rows
         self.seed, self.sample_calls = seed, 0
+        self.fresh_worlds, self.rollouts = fresh_worlds, 0
         self.buf = RolloutBuffer.allocate(self.T, env.W, env.N, env.C, env.F, env.device, obs_dtype)
         self.gen = torch.Generator(device=env.device); self.gen.manual_seed(seed)
         env.getAllObservations(out=(self.buf.obs[0], self.buf.vec[0]))
@@ -175,8 +178,12 @@ class VecPPOTrainer:
         """`Runner.run` (`runner.py:28-150`) for all worlds at once."""
         from ..vec_env import StepOut, gae, sample_actions
         b, env = self.buf, self.env
-        if self.sample_calls:        # continue from the last observation of the previous rollout
+        if self.fresh_worlds is not None and self.rollouts > 0:
+            env.reset(self.fresh_worlds(self.rollouts))
+            env.getAllObservations(out=(b.obs[0], b.vec[0]))
+        elif self.sample_calls:      # continue from the last observation of the previous rollout
             b.obs[0].copy_(b.obs[self.T]); b.vec[0].copy_(b.vec[self.T])
+        self.rollouts += 1
         for t in range(self.T):
             self._forward(b.obs[t], b.vec[t], b.ps[t], b.values[t], b.cost_values[t])
             sample_actions(b.ps[t], seed=self.seed, draw=self.sample_calls, out=b.actions[t])

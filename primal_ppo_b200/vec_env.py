@@ -61,12 +61,7 @@ class BatchedMapfGym:
         self.num_channel, self.use_da, self.use_hp = sc.num_channel, sc.use_da, sc.use_hp
         tape = sc.tape if (use_tape and sc.tape is not None) else None
 
-        def up(a):      # numpy arrays are uploaded; tensors of a DeviceScenario are used in place
-            if a is None:
-                return None
-            if isinstance(a, torch.Tensor):
-                return a.to(self.device).contiguous()
-            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        up = self._upload
         # scenario arrays are borrowed by the C side: keep them alive here
         self._sc = dict(obst=up(sc.obst), starts=up(sc.starts), goal_queue=up(sc.goal_queue), htrace=up(sc.htrace),
                         hlen=up(sc.hlen), hp5=up(sc.hp5), tape=up(tape),
@@ -96,6 +91,13 @@ class BatchedMapfGym:
         self.reset()
 
     # ------------------------------------------------------------------------------------------------------
+    def _upload(self, a):      # numpy arrays are uploaded; tensors of a DeviceScenario are used in place
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            return a.to(self.device).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -110,8 +112,25 @@ class BatchedMapfGym:
         except Exception:
             pass
 
-    def reset(self):
-        """``populateMap`` (mapf_gym.py:175-184): back to the scenario's starts / first goals / tick 0."""
+    def reset(self, scenario=None):
+        """``populateMap`` (mapf_gym.py:175-184): back to the scenario's starts / first goals / tick 0.  With ``scenario``
+        (same shapes as the one the env was created with) the worlds themselves are replaced — the reference builds a
+        fresh ``MapfGym()`` for every rollout (runner.py:30); with a ``DeviceScenario`` this involves no host copy."""
+        if scenario is not None:
+            scenario.validate()
+            sc = scenario
+            same = ((sc.num_worlds, sc.height, sc.width, sc.num_agents, sc.fov, sc.num_channel) ==
+                    (self.W, self.H, self.Wd, self.N, self.F, self.C)
+                    and int(sc.goal_queue.shape[2]) == int(self._sc["goal_queue"].shape[2])
+                    and int(sc.htrace.shape[1]) == int(self._sc["htrace"].shape[1])
+                    and bool(sc.use_da) == bool(self.use_da) and bool(sc.use_hp) == bool(self.use_hp)
+                    and (sc.dims is None) == (self._sc["dims"] is None) and (sc.hp5 is None) == (self._sc["hp5"] is None)
+                    and self._sc["tape"] is None and getattr(sc, "tape", None) is None)
+            if not same:
+                raise ValueError("reset(scenario): the new scenario must have the shapes / flags the env was created with")
+            up = self._upload
+            self._sc = dict(obst=up(sc.obst), starts=up(sc.starts), goal_queue=up(sc.goal_queue), htrace=up(sc.htrace),
+                            hlen=up(sc.hlen), hp5=up(sc.hp5), tape=None, tape_len=None, dims=up(sc.dims))
         s = self._sc
         sc = _cabi.MapfScenario(**{k: (None if v is None else v.data_ptr()) for k, v in s.items()})
         _cabi.check(self._lib.mapf_reset(self._h, C.byref(sc), self._stream()), "mapf_reset")

@@ -115,3 +115,31 @@ def test_gpu_evaluate_fixed_episodes_from_reference_fixture():
     res2 = evaluate_fixed_episodes(pol, sc, max_steps=48, greedy=True)
     res3 = evaluate_fixed_episodes(pol, sc, max_steps=48, greedy=True)
     assert np.array_equal(res2["per_episode"]["episodeReward"], res3["per_episode"]["episodeReward"])   # greedy is deterministic
+
+
+def test_gpu_fresh_worlds_every_rollout():
+    """reset(scenario): worlds replaced in place by a device-generated batch; the trainer does it before every rollout
+    (runner.py:30).  The env after reset(new) behaves like an env created on the new scenario."""
+    from primal_ppo_b200 import BatchedMapfGym, generate_scenario_device
+    from primal_ppo_b200.ppo import PPOConfig, ScrimpPolicy, VecPPOTrainer
+    gen = lambda k: generate_scenario_device(32, 40, 60, 4, kind="warehouse", size_range=(10, 40), queue_len=4, seed=100 + k)
+    env = BatchedMapfGym(gen(0), use_tape=False, seed=3)
+    a = torch.randint(0, 5, (5, 32, 4), dtype=torch.int8, device="cuda")
+    for t in range(5):
+        env.step_observe(a[t])
+    env.reset(gen(1))
+    ref = BatchedMapfGym(gen(1), use_tape=False, seed=3)
+    assert torch.equal(env.getAllObservations()[0], ref.getAllObservations()[0])
+    for t in range(5):
+        o1, ob1, _ = env.step_observe(a[t]); o2, ob2, _ = ref.step_observe(a[t])
+        assert torch.equal(ob1, ob2) and torch.equal(o1.reward, o2.reward) and torch.equal(o1.status, o2.status)
+    assert torch.equal(env.counters(), ref.counters())
+    with pytest.raises(ValueError):
+        env.reset(generate_scenario_device(16, 40, 60, 4, kind="warehouse", queue_len=4, seed=1))
+    torch.manual_seed(0)
+    tr = VecPPOTrainer(BatchedMapfGym(gen(0), use_tape=False), ScrimpPolicy().cuda().eval(), PPOConfig(n_steps=4, n_epochs=1),
+                       rows_per_minibatch=16, fresh_worlds=gen)
+    tr.collect(); first = tr.buf.obs[0].clone()
+    tr.collect()
+    assert not torch.equal(first, tr.buf.obs[0])
+    assert torch.equal(tr.buf.obs[0], BatchedMapfGym(gen(1), use_tape=False).getAllObservations()[0])
