@@ -63,3 +63,17 @@ def test_env_refuses_to_run_without_cuda():
     from primal_ppo_b200._cabi import MapfError
     with pytest.raises(MapfError):
         BatchedMapfGym(random_scenario(2, 8, 8, 2, seed=0))
+
+
+def test_header_is_plain_c_and_links(lib_path, tmp_path):
+    """include/mapf_b200.h compiles as C99 (no C++, no torch types) and a C program links against the library."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "mapf_b200.h"\n#include <stdio.h>\nint main(void) { MapfConfig c; MapfScenario s; MapfStepOut o; '
+                   'MapfGenConfig g; (void)c; (void)s; (void)o; (void)g; printf("%d %d\\n", mapf_abi_version(), mapf_create(0, 0)); return 0; }\n')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(lib_path)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(lib_path), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["1", "-2"]
