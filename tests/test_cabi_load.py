@@ -77,3 +77,22 @@ def test_header_is_plain_c_and_links(lib_path, tmp_path):
                     "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(lib_path), "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["1", "-2"]
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: without the built .so every entry into the product raises."""
+    from primal_ppo_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "libmapf_b200.so"))
+    with pytest.raises(_cabi.MapfError, match="no CPU fallback|missing"):
+        _cabi.load_library()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under primal_ppo_b200/ may import it."""
+    pkg = os.path.join(ROOT, "primal_ppo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
