@@ -142,7 +142,7 @@ def _draw_world(rng, case, mapf_gym):
         return ob, starts, goals, hseq
 
 
-def run_case(name, case, seed):
+def run_case(name, case, seed, out_dir=None):
     N = case["N"]
     mapf_gym, util, AP = load_reference(N)
     rng = np.random.default_rng(seed)
@@ -311,7 +311,7 @@ def run_case(name, case, seed):
                violated=st("violated"), shadow=st("shadow"), pos=st("pos"), goal=st("goal"),
                fixed=st("fixed"), vec=st("vec"), obs_shape=np.asarray(obs.shape, dtype=np.int64),
                obs_bits=np.packbits(obs.reshape(-1)), bfs0=bfs0, bfsT=bfsT)
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(out_dir or HERE, name + ".npz")
     np.savez_compressed(path, **out)
     nev = int(sum((w["tape"].size > 0) for w in worlds))
     print(f"{name}: {W} worlds, T={T}, N={N}, {Hm}x{Wm}; dropped {dropped}; "
