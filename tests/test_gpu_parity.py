@@ -135,7 +135,7 @@ def test_gpu_matches_oracle_config3_shape_40x40x32():
 
 
 @pytest.mark.parametrize("shape", [(1024, 40, 40, 32, 6), (512, 20, 20, 8, 6), (300, 8, 8, 8, 5), (64, 33, 65, 5, 6),
-                                   (40, 64, 64, 31, 6), (7, 7, 11, 1, 6)])
+                                   (40, 64, 64, 31, 6), (7, 7, 11, 1, 6), (5, 96, 80, 12, 6), (3, 128, 128, 32, 5)])
 def test_gpu_fused_step_observe_matches_oracle(shape):
     """mapf_step_observe (the fused launch) against the oracle, every step, incl. crowded worlds and odd shapes."""
     W, H, Wd, N, C = shape
@@ -169,7 +169,8 @@ def test_gpu_matches_oracle_crowded_fixactions_philox():
     _run_vs_oracle(sc, T=48)
 
 
-@pytest.mark.parametrize("shape", [(1, 7, 11, 1), (3, 12, 9, 6), (13, 10, 10, 2), (9, 33, 65, 5), (5, 64, 64, 31)])
+@pytest.mark.parametrize("shape", [(1, 7, 11, 1), (3, 12, 9, 6), (13, 10, 10, 2), (9, 33, 65, 5), (5, 64, 64, 31),
+                                   (4, 80, 80, 8), (3, 128, 128, 16), (6, 65, 64, 32)])
 def test_gpu_matches_oracle_ragged_shapes(shape):
     W, H, Wd, N = shape
     sc = random_scenario(W, H, Wd, N, density=(0.05, 0.2), queue_len=3, seed=W * 7 + N, num_channel=5 if N == 6 else 6)
