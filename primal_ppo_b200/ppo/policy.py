@@ -135,11 +135,25 @@ class ScrimpPolicy(nn.Module):
         e = self.enc
         if self.channels_last:
             obs = obs.contiguous(memory_format=torch.channels_last)
-        x = F.relu(e["c1"](obs)); x = F.relu(e["c1a"](x)); x = F.relu(e["c1b"](x))
-        x = F.max_pool2d(x, 2)
-        x = F.relu(e["c2"](x)); x = F.relu(e["c2a"](x)); x = F.relu(e["c2b"](x))
-        x = F.max_pool2d(x, 2)
-        x = F.relu(e["c3"](x).flatten(1))
+        if obs.is_cuda and self.channels_last and not torch.is_grad_enabled():
+            # rollout / evaluation path: cuDNN's fused convolution + bias + ReLU epilogue (one pass over the activations
+            # instead of two per layer; identical values).  It has no autograd formula, hence no_grad only.
+            dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else obs.dtype
+            x = obs.to(dt)
+
+            def cr(x, m):
+                return torch.cudnn_convolution_relu(x, m.weight.to(dt), m.bias.to(dt), m.stride, m.padding, m.dilation, 1)
+            x = cr(cr(cr(x, e["c1"]), e["c1a"]), e["c1b"])
+            x = F.max_pool2d(x, 2)
+            x = cr(cr(cr(x, e["c2"]), e["c2a"]), e["c2b"])
+            x = F.max_pool2d(x, 2)
+            x = cr(x, e["c3"]).flatten(1)
+        else:
+            x = F.relu(e["c1"](obs)); x = F.relu(e["c1a"](x)); x = F.relu(e["c1b"](x))
+            x = F.max_pool2d(x, 2)
+            x = F.relu(e["c2"](x)); x = F.relu(e["c2a"](x)); x = F.relu(e["c2b"](x))
+            x = F.max_pool2d(x, 2)
+            x = F.relu(e["c3"](x).flatten(1))
         g = F.relu(self.goal_fc(vector))
         x3 = torch.cat((x, g), dim=-1)
         h = self.mix2(F.relu(self.mix1(x3)))

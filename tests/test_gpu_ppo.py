@@ -143,3 +143,20 @@ def test_gpu_fresh_worlds_every_rollout():
     tr.collect()
     assert not torch.equal(first, tr.buf.obs[0])
     assert torch.equal(tr.buf.obs[0], BatchedMapfGym(gen(1), use_tape=False).getAllObservations()[0])
+
+
+def test_gpu_policy_fused_conv_relu_path_equals_plain_path():
+    """no_grad + channels_last takes cuDNN's fused conv+bias+ReLU; it must give the values of the autograd path."""
+    from primal_ppo_b200.ppo import ScrimpPolicy
+    torch.manual_seed(0)
+    pol = ScrimpPolicy().cuda().eval().use_channels_last()
+    obs = (torch.rand(96, 4, 6, 9, 9, device="cuda") < 0.15).float()
+    vec = torch.randn(96, 4, 4, device="cuda")
+    for dt in (None, torch.bfloat16):
+        with torch.autocast("cuda", dtype=dt, enabled=dt is not None):
+            with torch.no_grad():
+                a = pol(obs, vec)
+            b = pol(obs, vec)                       # grad enabled -> plain path
+        tol = 1e-5 if dt is None else 2e-2
+        assert float((a.policy.float() - b.policy.float()).abs().max()) < tol
+        assert float((a.value.float() - b.value.float()).abs().max()) < tol * 10
