@@ -94,6 +94,10 @@ cudaError_t launch_t(const EnvView &v, float *obs, float *vec, const ObsLayout &
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, observe_kernel<C_T, F_T, VEC4>, wpb * 32, smem);
     if (per_sm < 1) per_sm = 1;
+    // Store-dominated worlds (>= 32 KB of observations each) run best with FEWER resident warps: the HBM write path prefers
+    // fewer, longer write streams (write-pattern benchmark: 16 warps/SM beat 32 by 2 %), and this kernel has no other
+    // latency to hide.  In-process A/B at 40x40x32: 1 / 2 / 3 / 4 CTAs per SM = 0.613 / 0.608 / 0.612 / 0.622 ms.
+    if ((size_t)v.N * L.PB * (L.out_bf16 ? 2 : 4) >= 32768 && per_sm > 2) per_sm = 2;
     const int need = (v.W + wpb - 1) / wpb;
     const int blocks = need < sms * per_sm ? need : sms * per_sm;
     observe_kernel<C_T, F_T, VEC4><<<blocks, wpb * 32, smem, stream>>>(v, obs, vec, L, counter);

@@ -109,6 +109,9 @@ cudaError_t launch_t(const EnvView &v, const int8_t *actions, const MapfStepOut 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_observe_kernel<C_T, F_T, VEC4>, wpb * 32, smem);
     if (per_sm < 1) per_sm = 1;
+    // As in observe.cu fewer write streams help, but here the step phase needs warps to hide behind: in-process A/B at
+    // 40x40x32: 2 / 3 / 4 CTAs per SM = 0.772 / 0.722 / 0.731 ms.
+    if ((size_t)v.N * L.PB * (L.out_bf16 ? 2 : 4) >= 32768 && per_sm > 3) per_sm = 3;
     const int need = (v.W + wpb - 1) / wpb;
     const int blocks = need < sms * per_sm ? need : sms * per_sm;
     step_observe_kernel<C_T, F_T, VEC4><<<blocks, wpb * 32, smem, stream>>>(v, actions, out, obs, vec, L, per_warp, step_off, counter);
