@@ -19,8 +19,8 @@ namespace {
 using namespace sw;
 using namespace ow;
 
-template <int C_T, int F_T, bool VEC4>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+template <int C_T, int F_T, bool VEC4, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB)
 step_observe_kernel(const EnvView v, const int8_t *__restrict__ actions, const MapfStepOut out, float *__restrict__ obs,
                     float *__restrict__ vec, const ObsLayout L, const int per_warp, const int step_off,
                     int *__restrict__ work_counter) {
@@ -94,28 +94,38 @@ step_observe_kernel(const EnvView v, const int8_t *__restrict__ actions, const M
     finish_work(work_counter, gridDim.x * (blockDim.x >> 5), lane);
 }
 
-template <int C_T, int F_T, bool VEC4>
-cudaError_t launch_t(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
-                     const ObsLayout &L, int *counter, cudaStream_t stream) {
+template <int C_T, int F_T, bool VEC4, int MINB>
+cudaError_t launch_tb(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
+                      const ObsLayout &L, int *counter, cudaStream_t stream) {
     const int step_off = (int)L.total;
     const int per_warp = step_off + 32 * 5 * 4 + 32 * 4 + 5 * 32 + QRING;
     const int wpb = WARPS_PER_BLOCK;
     const size_t smem = (size_t)per_warp * wpb;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(step_observe_kernel<C_T, F_T, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = step_observe_kernel<C_T, F_T, VEC4, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_observe_kernel<C_T, F_T, VEC4>, wpb * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem);
     if (per_sm < 1) per_sm = 1;
-    // As in observe.cu fewer write streams help, but here the step phase needs warps to hide behind: in-process A/B at
-    // 40x40x32: 2 / 3 / 4 CTAs per SM = 0.772 / 0.722 / 0.731 ms.
-    if ((size_t)v.N * L.PB * (L.out_bf16 ? 2 : 4) >= 32768 && per_sm > 3) per_sm = 3;
+    if (per_sm > MINB) per_sm = MINB;
     const int need = (v.W + wpb - 1) / wpb;
     const int blocks = need < sms * per_sm ? need : sms * per_sm;
-    step_observe_kernel<C_T, F_T, VEC4><<<blocks, wpb * 32, smem, stream>>>(v, actions, out, obs, vec, L, per_warp, step_off, counter);
+    kern<<<blocks, wpb * 32, smem, stream>>>(v, actions, out, obs, vec, L, per_warp, step_off, counter);
     return cudaGetLastError();
+}
+
+// As in observe.cu fewer write streams help store-dominated worlds (>= 32 KB of observations each), but here the step
+// phase needs warps to hide behind: in-process A/B at 40x40x32: 2 / 3 / 4 CTAs per SM = 0.772 / 0.722 / 0.731 ms.  The
+// 3-CTA instantiation is also COMPILED for 3 CTAs (80 registers instead of 64, no spills): 0.706 vs 0.721 ms.
+template <int C_T, int F_T, bool VEC4>
+cudaError_t launch_t(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
+                     const ObsLayout &L, int *counter, cudaStream_t stream) {
+    const bool big = (size_t)v.N * L.PB * (L.out_bf16 ? 2 : 4) >= 32768;
+    if (big) return launch_tb<C_T, F_T, VEC4, 3>(v, actions, out, obs, vec, L, counter, stream);
+    return launch_tb<C_T, F_T, VEC4, 4>(v, actions, out, obs, vec, L, counter, stream);
 }
 
 }  // namespace
