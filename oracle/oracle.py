@@ -27,10 +27,21 @@ def oracle_lib_path() -> str:
 def build_oracle(force: bool = False) -> str:
     """gcc -O2 -fopenmp -ffp-contract=off: no FMA contraction so that GAE rounds like NumPy."""
     os.makedirs(_BUILD, exist_ok=True)
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
-        cmd = ["gcc", "-O2", "-std=c11", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
-               "-fvisibility=hidden", "-o", _LIB, _SRC, "-lm"]
-        subprocess.run(cmd, check=True)
+
+    def stale():
+        return force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC)
+    if stale():
+        import fcntl
+        with open(os.path.join(_BUILD, ".lock"), "w") as lock:       # concurrent test / bench processes: one builds
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if stale():
+                    cmd = ["gcc", "-O2", "-std=c11", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                           "-fvisibility=hidden", "-o", _LIB + ".tmp", _SRC, "-lm"]
+                    subprocess.run(cmd, check=True)
+                    os.replace(_LIB + ".tmp", _LIB)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _LIB
 
 

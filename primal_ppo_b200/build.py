@@ -1,6 +1,7 @@
 """Builds libmapf_b200.so (the C-ABI shared library of include/mapf_b200.h) in-tree with nvcc for sm_100a."""
 from __future__ import annotations
 
+import fcntl
 import os
 import subprocess
 import sys
@@ -24,15 +25,28 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not (force or _stale()):
         return LIB_PATH
+    # several ranks of one job may get here at once (torchrun): one of them builds, the others wait and re-check
+    with open(os.path.join(_PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not (force or _stale()):
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libmapf_b200.so")
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)          # atomic: a concurrently loading process never sees a partial file
     return LIB_PATH
 
 
