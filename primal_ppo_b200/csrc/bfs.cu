@@ -144,6 +144,162 @@ bfs_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long l
     finish_work(work_counter, gridDim.x * (blockDim.x >> 5), lane);
 }
 
+// ---- second formulation: cell-string layout, Gray-coded level planes, no per-cell stores in the level loop ----------
+//
+// ncu of the kernel above (40x40, `profiles/r01_ncu_full_raw_final_bfs.csv`): 60 % of its warp instructions are the
+// per-bit `tile[cell] = level` loops (19 % / 10 % of the lanes active), 35 % the wavefront update.  This kernel never
+// writes a level per cell.  Layout: a map is ONE bit string, bit i = cell i = r*Wd + c (exactly the layout of
+// `obst_pack`, so the free mask is a plain load); G lanes share a map, each lane owns NWL consecutive 32-bit words.
+// Column neighbours are the string shifted by 1 (masked at row ends), row neighbours the string shifted by Wd
+// = 32*WO + sb: funnel shifts over the lane's words plus the WO+1 words of each neighbouring lane (shuffles).
+// Levels are kept bit-sliced: plane b of a cell = bit b of the Gray code of its distance.  All unvisited cells carry
+// the code of the current level; advancing the level flips ONE plane (b = ctz(level+1)) for the unvisited cells
+// (NWL load-xor-stores in shared memory per level), a visited cell simply stops being flipped.  When the wavefront
+// dies: Gray -> binary by a suffix XOR over the planes, obstacles forced to 0xffff (-1) and unreached cells to 0xfffe
+// (-2) in plane space, a 16x16 bit-matrix transpose per word turns 16 planes x 32 cells into 32 int16, and the lane
+// stores its 64-byte run with 16-byte vector stores straight from registers (no tile, no TMA store).
+template <int NWL, int WO>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+bfs_gray_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const long long n_maps_in,
+                const int32_t *__restrict__ n_dev, int16_t *__restrict__ out, const int G, const int NB,
+                const int scatter, int *__restrict__ work_counter) {
+    extern __shared__ __align__(16) uint32_t planes_all[];
+    static_assert(NWL >= WO + 1, "a row neighbour must live in the lane itself or the adjacent lane");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MPW = 32 / G, grp = lane / G, gl = lane % G;
+    const int Wd = v.Wd, cells = v.H * v.Wd, sb = Wd & 31;
+    // plane b, word j of this lane: pl[(b * NWL + j) * 32]; planes NB and NB+1 stash the free / unreached masks
+    uint32_t *pl = planes_all + (size_t)warp * (NB + 2) * NWL * 32 + lane;
+    const long long n_maps = n_dev ? (long long)*n_dev : n_maps_in;
+    const int cell0 = gl * NWL * 32;                                  // first cell of this lane's words
+
+    // masks of the cells that are not in column 0 / not in column Wd-1 (the +-1 shifts must not wrap between rows)
+    uint32_t nc0[NWL], ncl[NWL];
+#pragma unroll
+    for (int j = 0; j < NWL; ++j) {
+        const int i0 = cell0 + 32 * j, c0 = i0 % Wd;
+        uint32_t a = 0, b = 0;
+        for (int t = (Wd - c0) % Wd; t < 32; t += Wd) a |= 1u << t;              // column 0
+        for (int t = (Wd - 1 - c0 + Wd) % Wd; t < 32; t += Wd) b |= 1u << t;     // column Wd-1
+        nc0[j] = ~a; ncl[j] = ~b;
+    }
+
+    for (;;) {
+        const long long base = claim_work(work_counter, MPW, lane);
+        if (base >= n_maps) break;
+        const long long m = base + grp;
+        const bool valid = m < n_maps;
+        const long long fid = valid ? (agent_list ? (long long)agent_list[m] : m) : 0;
+        const int w = (int)(fid / v.N);
+        const uint32_t gw = reinterpret_cast<const uint32_t *>(v.goal)[fid];
+        const int gi = valid ? (int)(int16_t)(gw & 0xffff) * Wd + (int)(int16_t)(gw >> 16) : -1;   // goal cell
+        const uint32_t *ob = v.obst_pack + (size_t)w * v.PW;
+
+        uint32_t freeb[NWL], fm[NWL], fr[NWL];
+#pragma unroll
+        for (int j = 0; j < NWL; ++j) {
+            const int k = gl * NWL + j, i0 = cell0 + 32 * j;
+            uint32_t x = 0;
+            if (valid && k < v.PW && i0 < cells) {
+                x = ~__ldg(ob + k);
+                if (cells - i0 < 32) x &= (1u << (cells - i0)) - 1u;
+            }
+            const uint32_t g = (gi >= i0 && gi < i0 + 32) ? (1u << (gi - i0)) : 0u;
+            fr[j] = g;
+            freeb[j] = x | g;            // the goal cell gets its 0 even when it is not free (mapf_gym.py:216)
+            fm[j] = x & ~g;              // free and not visited yet
+        }
+        int level = 0;                   // distance of the current frontier
+        for (;;) {
+            // words of the neighbouring lanes of the same map
+            uint32_t pv[WO + 1], nx_[WO + 1];                         // pv[t] = word NWL-1-t of lane-1, nx_[t] = word t of lane+1
+#pragma unroll
+            for (int t = 0; t <= WO; ++t) {
+                pv[t] = __shfl_up_sync(FULL, fr[NWL - 1 - t], 1, G);
+                nx_[t] = __shfl_down_sync(FULL, fr[t], 1, G);
+                if (gl == 0) pv[t] = 0;
+                if (gl == G - 1) nx_[t] = 0;
+            }
+            auto word = [&](int idx) -> uint32_t {                    // idx is a compile-time constant after unrolling
+                if (idx >= 0 && idx < NWL) return fr[idx];
+                if (idx < 0 && -idx - 1 <= WO) return pv[-idx - 1];
+                if (idx >= NWL && idx - NWL <= WO) return nx_[idx - NWL];
+                return 0u;
+            };
+            uint32_t nw[NWL], any = 0;
+#pragma unroll
+            for (int j = 0; j < NWL; ++j) {
+                const uint32_t left = __funnelshift_l(word(j - 1), fr[j], 1) & nc0[j];        // from cell i-1
+                const uint32_t right = __funnelshift_r(fr[j], word(j + 1), 1) & ncl[j];       // from cell i+1
+                const uint32_t up = __funnelshift_l(word(j - WO - 1), word(j - WO), sb);      // from cell i-Wd
+                const uint32_t down = __funnelshift_r(word(j + WO), word(j + WO + 1), sb);    // from cell i+Wd
+                nw[j] = (left | right | up | down) & fm[j];
+                any |= nw[j];
+            }
+            if (!__any_sync(FULL, any != 0)) break;
+            // level -> level+1: one Gray plane flips for every cell that was unvisited (the new frontier included)
+            const int nl = level + 1, b = __ffs(nl) - 1;
+            uint32_t *pb = pl + (size_t)b * NWL * 32;
+            if (nl == (1 << b)) {                                     // first touch of this plane: it was all zero
+#pragma unroll
+                for (int j = 0; j < NWL; ++j) pb[j * 32] = fm[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < NWL; ++j) pb[j * 32] ^= fm[j];
+            }
+#pragma unroll
+            for (int j = 0; j < NWL; ++j) { fr[j] = nw[j]; fm[j] &= ~nw[j]; }
+            level = nl;
+        }
+        // planes in use: those of codes up to `level` (warp-uniform: the loop runs until the slowest map is done)
+        const int nb = 32 - __clz(level);
+#pragma unroll
+        for (int j = 0; j < NWL; ++j) { pl[((size_t)NB * NWL + j) * 32] = freeb[j]; pl[((size_t)(NB + 1) * NWL + j) * 32] = fm[j]; }
+        int16_t *dst = out + (size_t)(scatter ? fid : m) * cells;
+#pragma unroll 1
+        for (int j = 0; j < NWL; ++j) {
+            const int i0 = cell0 + 32 * j;
+            if (!valid || i0 >= cells) continue;
+            uint32_t P[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) P[q] = q < nb ? pl[((size_t)q * NWL + j) * 32] : 0u;
+#pragma unroll
+            for (int q = 14; q >= 0; --q) P[q] ^= P[q + 1];                           // Gray -> binary
+            const uint32_t ob_ = ~pl[((size_t)NB * NWL + j) * 32], un = pl[((size_t)(NB + 1) * NWL + j) * 32];
+            P[0] = (P[0] | ob_) & ~un;                                                // -1 = 0xffff, -2 = 0xfffe
+#pragma unroll
+            for (int q = 1; q < 16; ++q) P[q] |= ob_ | un;
+            // 16x16 bit transpose of both halves at once: afterwards P[q] = level(cell q) | level(cell 16+q) << 16
+#define MAPF_TSTAGE(S, MK)                                                      \
+            _Pragma("unroll") for (int q = 0; q < 16; ++q) {                        \
+                if ((q & S) == 0) {                                                 \
+                    const uint32_t t = ((P[q] >> S) ^ P[q + S]) & MK;               \
+                    P[q + S] ^= t;                                                  \
+                    P[q] ^= t << S;                                                 \
+                }                                                                   \
+            }
+            MAPF_TSTAGE(8, 0x00ff00ffu) MAPF_TSTAGE(4, 0x0f0f0f0fu) MAPF_TSTAGE(2, 0x33333333u) MAPF_TSTAGE(1, 0x55555555u)
+#undef MAPF_TSTAGE
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + i0);
+            const int nvec = (cells - i0 >= 32) ? 4 : (cells - i0) >> 3;              // cells % 8 == 0 (launcher)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (h >= nvec) continue;
+                const int q = (h & 1) * 8;                                            // cells 8h .. 8h+7
+                const uint32_t sel = (h < 2) ? 0x5410u : 0x7632u;                     // low halves: cells 0..15; high: 16..31
+                uint4 o;
+                o.x = __byte_perm(P[q + 0], P[q + 1], sel);
+                o.y = __byte_perm(P[q + 2], P[q + 3], sel);
+                o.z = __byte_perm(P[q + 4], P[q + 5], sel);
+                o.w = __byte_perm(P[q + 6], P[q + 7], sel);
+                d4[h] = o;
+            }
+        }
+        __syncwarp();
+    }
+    finish_work(work_counter, gridDim.x * (blockDim.x >> 5), lane);
+}
+
 // Compaction of arrivals: flat ids (w*N+i) of agents with goals_reached == 1.  Order is irrelevant (each refreshed
 // map is written to its own slot), so one atomicAdd per warp on a device counter is enough.
 __global__ void arrivals_kernel(const uint8_t *__restrict__ goals, const long long n, int32_t *__restrict__ list,
@@ -186,6 +342,45 @@ cudaError_t launch_bfs_t(const EnvView &v, const int32_t *agent_list, long long 
     return cudaGetLastError();
 }
 
+template <int NWL, int WO>
+cudaError_t launch_bfs_gray_t(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
+                              int G, int scatter, int *work_counter, cudaStream_t stream) {
+    const int cells = v.H * v.Wd, MPW = 32 / G;
+    int NB = 1;
+    while ((1 << NB) <= cells) ++NB;                                  // levels < cells < 2^NB
+    const size_t per_warp = (size_t)(NB + 2) * NWL * 128;
+    int wpb = WARPS_PER_BLOCK;
+    while (wpb > 1 && per_warp * wpb > 110 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    cudaError_t e = cudaFuncSetAttribute(bfs_gray_kernel<NWL, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_gray_kernel<NWL, WO>, wpb * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const long long need = (n + (long long)wpb * MPW - 1) / ((long long)wpb * MPW);
+    const int blocks = (int)(need < (long long)sms * per_sm ? need : (long long)sms * per_sm);
+    if (blocks <= 0) return cudaSuccess;
+    bfs_gray_kernel<NWL, WO><<<blocks, wpb * 32, smem, stream>>>(v, agent_list, n, n_dev, out, G, NB, scatter, work_counter);
+    return cudaGetLastError();
+}
+
+// Lanes per map and words per lane of the cell-string kernel: the smallest G of 8/16/32 with <= 4 words per lane
+// (G = 32 takes whatever is left, up to 16 words for 128x128), words rounded up to an instantiated count.
+bool bfs_gray_shape(const EnvView &v, int &G, int &NWL, int &WO) {
+    const int cells = v.H * v.Wd;
+    WO = v.Wd >> 5;
+    const int force = (v.dbg_flags >> 17) & 3;                        // MAPF_DBG_FLAGS bits 17..18: force G = 8/16/32
+    G = 8;
+    while (G < 32 && (cells + 32 * G - 1) / (32 * G) > 4) G *= 2;
+    if (force) G = 4 << force;
+    NWL = (cells + 32 * G - 1) / (32 * G);
+    if (NWL < WO + 1) NWL = WO + 1;
+    if (NWL > 8) NWL = NWL <= 10 ? 10 : NWL <= 12 ? 12 : 16;
+    return NWL * 32 * G >= cells && NWL <= 16;
+}
+
 }  // namespace
 
 cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
@@ -193,6 +388,27 @@ cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n,
     // lanes per map: the smallest of 8/16/32 that keeps <= 5 rows per lane AND at most ~6.5 KB of int16 tiles per warp,
     // so that 32 warps fit an SM.  The kernel is issue/latency-bound (serial wavefront), and occupancy buys more than
     // the extra maps per warp: 40x40 runs 1.31x faster with 16 lanes per map than with 8, 80x80 1.7x faster with 32.
+    // cell-string kernel whenever the maps can leave as 16-byte vectors (H*Wd % 8 == 0, aligned output);
+    // MAPF_DBG_FLAGS bit 16 keeps the row-word kernel for A/B runs
+    {
+        int G, NWL, WO;
+        const bool vec_ok = ((v.H * v.Wd) % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        if (vec_ok && !(v.dbg_flags & (1 << 16)) && bfs_gray_shape(v, G, NWL, WO)) {
+#define GCASE(nwl, wo) if (NWL == nwl && WO == wo) return launch_bfs_gray_t<nwl, wo>(v, agent_list, n, n_dev, out, G, scatter, work_counter, stream);
+#define GCASES0(nwl) GCASE(nwl, 0)
+#define GCASES1(nwl) GCASES0(nwl) GCASE(nwl, 1)
+#define GCASES2(nwl) GCASES1(nwl) GCASE(nwl, 2)
+#define GCASES3(nwl) GCASES2(nwl) GCASE(nwl, 3)
+#define GCASES4(nwl) GCASES3(nwl) GCASE(nwl, 4)
+            GCASES0(1) GCASES1(2) GCASES2(3) GCASES3(4) GCASES4(5) GCASES4(6) GCASES4(7) GCASES4(8) GCASES4(10) GCASES4(12) GCASES4(16)
+#undef GCASES4
+#undef GCASES3
+#undef GCASES2
+#undef GCASES1
+#undef GCASES0
+#undef GCASE
+        }
+    }
     const int tile_b = ((v.H * v.Wd * 2 + 127) / 128) * 128;
     int G = 8;
     while (G < 32 && ((v.H + G - 1) / G > 5 || (32 / G) * tile_b > 6656)) G *= 2;
