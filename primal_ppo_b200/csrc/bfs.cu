@@ -25,6 +25,14 @@ __device__ __forceinline__ void bulk_store_g2s_commit_wait(void *gdst, const voi
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// prmt.b32 in its default mode: bit 3 of a selector nibble replicates the sign of the selected byte (__byte_perm only
+// documents the low three bits)
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // G lanes cooperate on one map (32/G maps per warp), R consecutive rows per lane, NW 32-bit words per row.
 template <int G, int R, int NW>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
@@ -260,12 +268,49 @@ bfs_gray_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const l
         for (int j = 0; j < NWL; ++j) {
             const int i0 = cell0 + 32 * j;
             if (!valid || i0 >= cells) continue;
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + i0);
+            const int nvec = (cells - i0 >= 32) ? 4 : (cells - i0) >> 3;              // cells % 8 == 0 (launcher)
+            const uint32_t ob_ = ~pl[((size_t)NB * NWL + j) * 32], un = pl[((size_t)(NB + 1) * NWL + j) * 32];
+            if (nb <= 7) {
+                // levels < 128: 8 planes, an 8x8 bit transpose of the four bytes at once, then sign-extending byte
+                // permutes widen level / 0xff (-1) / 0xfe (-2) to int16
+                uint32_t Q[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) Q[q] = q < nb ? pl[((size_t)q * NWL + j) * 32] : 0u;
+#pragma unroll
+                for (int q = 6; q >= 0; --q) Q[q] ^= Q[q + 1];                        // Gray -> binary
+                Q[0] = (Q[0] | ob_) & ~un;
+#pragma unroll
+                for (int q = 1; q < 8; ++q) Q[q] |= ob_ | un;
+#define MAPF_TSTAGE8(S, MK)                                                     \
+                _Pragma("unroll") for (int q = 0; q < 8; ++q) {                     \
+                    if ((q & S) == 0) {                                             \
+                        const uint32_t t = ((Q[q] >> S) ^ Q[q + S]) & MK;           \
+                        Q[q + S] ^= t;                                              \
+                        Q[q] ^= t << S;                                             \
+                    }                                                               \
+                }
+                MAPF_TSTAGE8(4, 0x0f0f0f0fu) MAPF_TSTAGE8(2, 0x33333333u) MAPF_TSTAGE8(1, 0x55555555u)
+#undef MAPF_TSTAGE8
+                // now byte h of Q[q] = level of cell 8h + q
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (h >= nvec) continue;
+                    const uint32_t sel = (uint32_t)h | ((uint32_t)(h | 8) << 4) | ((uint32_t)(4 + h) << 8) | ((uint32_t)((4 + h) | 8) << 12);
+                    uint4 o;
+                    o.x = prmt_sx(Q[0], Q[1], sel);
+                    o.y = prmt_sx(Q[2], Q[3], sel);
+                    o.z = prmt_sx(Q[4], Q[5], sel);
+                    o.w = prmt_sx(Q[6], Q[7], sel);
+                    d4[h] = o;
+                }
+                continue;
+            }
             uint32_t P[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) P[q] = q < nb ? pl[((size_t)q * NWL + j) * 32] : 0u;
 #pragma unroll
             for (int q = 14; q >= 0; --q) P[q] ^= P[q + 1];                           // Gray -> binary
-            const uint32_t ob_ = ~pl[((size_t)NB * NWL + j) * 32], un = pl[((size_t)(NB + 1) * NWL + j) * 32];
             P[0] = (P[0] | ob_) & ~un;                                                // -1 = 0xffff, -2 = 0xfffe
 #pragma unroll
             for (int q = 1; q < 16; ++q) P[q] |= ob_ | un;
@@ -280,8 +325,6 @@ bfs_gray_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const l
             }
             MAPF_TSTAGE(8, 0x00ff00ffu) MAPF_TSTAGE(4, 0x0f0f0f0fu) MAPF_TSTAGE(2, 0x33333333u) MAPF_TSTAGE(1, 0x55555555u)
 #undef MAPF_TSTAGE
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst + i0);
-            const int nvec = (cells - i0 >= 32) ? 4 : (cells - i0) >> 3;              // cells % 8 == 0 (launcher)
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 if (h >= nvec) continue;
@@ -349,16 +392,22 @@ cudaError_t launch_bfs_gray_t(const EnvView &v, const int32_t *agent_list, long 
     int NB = 1;
     while ((1 << NB) <= cells) ++NB;                                  // levels < cells < 2^NB
     const size_t per_warp = (size_t)(NB + 2) * NWL * 128;
-    int wpb = WARPS_PER_BLOCK;
-    while (wpb > 1 && per_warp * wpb > 110 * 1024) wpb >>= 1;
-    const size_t smem = per_warp * wpb;
-    cudaError_t e = cudaFuncSetAttribute(bfs_gray_kernel<NWL, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bfs_gray_kernel<NWL, WO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(per_warp * WARPS_PER_BLOCK > 200 * 1024 ? 200 * 1024 : per_warp * WARPS_PER_BLOCK));
     if (e != cudaSuccess) return e;
-    int dev = 0, sms = 148, per_sm = 1;
+    int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_gray_kernel<NWL, WO>, wpb * 32, smem);
-    if (per_sm < 1) per_sm = 1;
+    // the planes are the occupancy limit: take the CTA size that keeps the most warps resident
+    int wpb = 1, per_sm = 1, best = 0;
+    for (int cand = WARPS_PER_BLOCK; cand >= 1; --cand) {
+        if (per_warp * cand > 200 * 1024) continue;
+        int k = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, bfs_gray_kernel<NWL, WO>, cand * 32, per_warp * cand) != cudaSuccess) continue;
+        if (k * cand > best) { best = k * cand; wpb = cand; per_sm = k; }
+    }
+    if (best == 0) return cudaErrorInvalidConfiguration;
+    const size_t smem = per_warp * wpb;
     const long long need = (n + (long long)wpb * MPW - 1) / ((long long)wpb * MPW);
     const int blocks = (int)(need < (long long)sms * per_sm ? need : (long long)sms * per_sm);
     if (blocks <= 0) return cudaSuccess;
@@ -366,14 +415,15 @@ cudaError_t launch_bfs_gray_t(const EnvView &v, const int32_t *agent_list, long 
     return cudaGetLastError();
 }
 
-// Lanes per map and words per lane of the cell-string kernel: the smallest G of 8/16/32 with <= 4 words per lane
+// Lanes per map and words per lane of the cell-string kernel: the smallest G of 8/16/32 with <= 8 words per lane
+// (measured at 40x40: 8 lanes x 7 words 0.90 ms, 16 x 4 1.07 ms, 32 x 2 1.20 ms for 262 144 maps)
 // (G = 32 takes whatever is left, up to 16 words for 128x128), words rounded up to an instantiated count.
 bool bfs_gray_shape(const EnvView &v, int &G, int &NWL, int &WO) {
     const int cells = v.H * v.Wd;
     WO = v.Wd >> 5;
     const int force = (v.dbg_flags >> 17) & 3;                        // MAPF_DBG_FLAGS bits 17..18: force G = 8/16/32
     G = 8;
-    while (G < 32 && (cells + 32 * G - 1) / (32 * G) > 4) G *= 2;
+    while (G < 32 && (cells + 32 * G - 1) / (32 * G) > 8) G *= 2;
     if (force) G = 4 << force;
     NWL = (cells + 32 * G - 1) / (32 * G);
     if (NWL < WO + 1) NWL = WO + 1;
