@@ -1,16 +1,22 @@
-// bfs.cu — BFS distance-to-goal maps: bit-parallel frontier wavefront, one warp per map.
+// bfs.cu — BFS distance-to-goal maps, bit-parallel frontier wavefront.
 //
 // Replaces MapfGym.makeBfsMap (mapf_gym.py:211-244): 4-connected BFS from the agent's goal over free cells;
 // -1 obstacle, -2 unreached, >= 0 distance (the goal cell is written 0 even when it is not free, as the reference
 // does).  The reference computes one map per agent at reset and on every goal arrival (:183, :627).
 //
-// Layout: the world's rows are bit masks held in registers; G lanes share one map (G = 8 for H <= 40, so a warp runs
-// four maps at once), R consecutive rows per lane, NW 32-bit words per row.  One BFS level is
+// Two formulations live here:
+//   bfs_gray_kernel  (shipped path)  the map as one cell string, Gray-coded level planes, no per-cell level stores;
+//                                    see the comment above the kernel.
+//   bfs_kernel       (fallback)      rows as words, an int16 tile in shared memory, per-bit level writes, one TMA bulk
+//                                    store per map; takes the maps that cannot leave as 16-byte vectors.
+//
+// bfs_kernel layout: the world's rows are bit masks held in registers; G lanes share one map, R consecutive rows per
+// lane, NW 32-bit words per row.  One BFS level is
 //     next = ((f << 1) | (f >> 1) | f_row_above | f_row_below) & free & ~visited
 // with the rows above/below a lane's block fetched by warp shuffles.  Newly reached cells get the level written into
 // an int16 tile in shared memory; when the wavefront dies the tile (H*Wd*2 bytes, 3200 B for 40x40) leaves with ONE
-// TMA bulk store (cp.async.bulk.global.shared::cta) issued by lane 0, so the warp spends no store instructions on
-// the output.  Algorithmic HBM traffic per map: 2*H*Wd B written, the world's obstacle bit rows read (shared by its N maps).
+// TMA bulk store (cp.async.bulk.global.shared::cta) issued by lane 0.
+// Algorithmic HBM traffic per map (both kernels): 2*H*Wd B written, the world's obstacle bit matrix read (shared by its N maps).
 #include "common.cuh"
 
 namespace mapf {

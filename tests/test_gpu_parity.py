@@ -354,6 +354,23 @@ def test_gpu_bfs_deep_mazes():
     _eq(_np(env.bfs_maps(agent_ids=ids)), ref.reshape(W * N, H, H)[ids.cpu().numpy()], "listed maps")
 
 
+@pytest.mark.parametrize("shape", [(8, 5), (8, 8), (6, 12), (16, 31), (8, 32), (24, 33), (40, 40), (17, 40), (12, 64),
+                                   (9, 96), (30, 100), (8, 127), (25, 128), (64, 64), (100, 72), (7, 9), (11, 13)])
+def test_gpu_bfs_map_shapes(shape):
+    """Row lengths on both sides of every 32-bit word boundary (the row-neighbour shift of the cell-string kernel is
+    32*(Wd/32) + Wd%32 bits), cell counts that do and do not fill the last word, and shapes whose maps cannot leave as
+    16-byte vectors (H*Wd % 8 != 0: the row-word kernel takes them)."""
+    H, Wd = shape
+    W, N = 6, 5
+    sc = random_scenario(W, H, Wd, N, density=(0.0, 0.35), queue_len=2, seed=1000 + H * 131 + Wd, fov=3)
+    orc = OracleMapfGym(sc, threads=4, use_tape=False)
+    env = _env(sc, use_tape=False)
+    ref = orc.bfs_maps()
+    _eq(_np(env.bfs_maps()), ref, f"bfs {H}x{Wd}")
+    ids = torch.tensor([W * N - 1, 0, 7, 7, 3], dtype=torch.int32).cuda()      # listed (and repeated) maps
+    _eq(_np(env.bfs_maps(agent_ids=ids)), ref.reshape(W * N, H, Wd)[ids.cpu().numpy()], f"listed maps {H}x{Wd}")
+
+
 def test_gpu_bfs_refresh_in_place():
     sc = random_scenario(256, 40, 40, 32, density=(0.0, 0.3), queue_len=8, seed=21, unique_maps=32)
     orc = OracleMapfGym(sc, threads=8, use_tape=False)
