@@ -280,6 +280,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    hb = env.make_host_buffers(with_obs=False, action_slots=8)     # one pinned slab: results + the runner's action ring
+    for k, r in enumerate(ring):
+        hb["action_ring"][k].copy_(r)
+    host_ring = [hb["action_ring"][k] for k in range(8)]
+
+    def run_e2e(n_calls):
+        """n_calls of the host-buffer C-ABI call, wall clock, after 3 untimed calls.  Returns (seconds, h2d, d2h bytes)."""
+        for i in range(3):
+            env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])
+        barrier()
+        t0 = time.perf_counter()
+        stamps = []
+        for i in range(n_calls):
+            h2d_, d2h_ = env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])   # the runner's pinned host action array
+            _ = float(hb["reward"][0, 0])                            # the step's result is read on the host
+            stamps.append(time.perf_counter())
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if os.environ.get("BENCH_E2E_DEBUG"):
+            d = [round((b - a) * 1e3, 3) for a, b in zip([t0] + stamps[:-1], stamps)]
+            print("e2e per-call ms:", d, "mean", round(dt / n_calls * 1e3, 3), file=sys.stderr)
+        return dt, h2d_, d2h_
+
     # ---------------- device-resident throughput (value): one fused step+observe launch per step ------------------
     clk = ClockSampler(local_rank).start()          # running before the warm-up so that it has samples in the timed region
     for i in range(Wu):
@@ -321,18 +344,8 @@ def main():
     obs_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evk]))
 
     # ---------------- end to end through the host-buffer C-ABI call ---------------------------------------------
-    hb = env.make_host_buffers(with_obs=False)
-    host_ring = [r.cpu().pin_memory() for r in ring]
     Ke = max(3, min(K, 20))
-    for i in range(3):
-        env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        h2d, d2h = env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])   # the runner's pinned host action array
-        _ = float(hb["reward"][0, 0])                                # the step's result is read on the host
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    e2e_s, h2d, d2h = run_e2e(Ke)
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

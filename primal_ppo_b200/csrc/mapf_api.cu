@@ -426,7 +426,14 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
         CU(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
         e->staging = true;
     }
+    // MAPF_DBG_FLAGS bit 20: print the device timeline of this call (timing events; experiments only)
+    const bool tl = (v.dbg_flags >> 20) & 1;
+    static cudaEvent_t t_ev[6];
+    static bool t_init = false;
+    if (tl && !t_init) { for (auto &x : t_ev) cudaEventCreate(&x); t_init = true; }
+    if (tl) cudaEventRecord(t_ev[0], s);
     CU(cudaMemcpyAsync(e->d_actions, actions_host, WN, cudaMemcpyHostToDevice, s));
+    if (tl) cudaEventRecord(t_ev[1], s);
     MapfStepOut o = e->d_out;                                   // only compute what the caller asked for
     if (!out->status) o.status = nullptr;
     if (!out->reward) o.reward = nullptr;
@@ -445,8 +452,11 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
     // prefetch and tail efficiency).  Hence the two-kernel form here, the fused launch for device-resident callers.
     cudaStream_t cs = e->copy_stream;
     CU(cudaEventRecord(e->ev_step, s));
+    if (tl) cudaEventRecord(t_ev[2], s);
     CU(cudaStreamWaitEvent(cs, e->ev_step, 0));
+    if (tl) cudaEventRecord(t_ev[4], cs);
     CU(launch_observe(v, obs_dev, vec_dev, e->d_work, s));
+    if (tl) cudaEventRecord(t_ev[3], s);
     if (out->status) CU(cudaMemcpyAsync(out->status, o.status, WN, cudaMemcpyDeviceToHost, cs));
     if (out->reward) CU(cudaMemcpyAsync(out->reward, o.reward, WN * 4, cudaMemcpyDeviceToHost, cs));
     if (out->cost) CU(cudaMemcpyAsync(out->cost, o.cost, WN * 4, cudaMemcpyDeviceToHost, cs));
@@ -456,11 +466,19 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
     if (out->shadow_goals) CU(cudaMemcpyAsync(out->shadow_goals, o.shadow_goals, W * 4, cudaMemcpyDeviceToHost, cs));
     if (out->fixed_actions) CU(cudaMemcpyAsync(out->fixed_actions, o.fixed_actions, WN, cudaMemcpyDeviceToHost, cs));
     CU(cudaEventRecord(e->ev_copied, cs));
+    if (tl) cudaEventRecord(t_ev[5], cs);
     const size_t PB = (size_t)v.C * v.F * v.F;
     if (obs_host) CU(cudaMemcpyAsync(obs_host, obs_dev, WN * PB * 4, cudaMemcpyDeviceToHost, s));
     if (vec_host) CU(cudaMemcpyAsync(vec_host, vec_dev, WN * 16, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamWaitEvent(s, e->ev_copied, 0));
     CU(cudaStreamSynchronize(s));
+    if (tl) {
+        float a = 0, b = 0, c = 0, d = 0, f = 0;
+        cudaEventElapsedTime(&a, t_ev[0], t_ev[1]); cudaEventElapsedTime(&b, t_ev[1], t_ev[2]);
+        cudaEventElapsedTime(&c, t_ev[2], t_ev[3]); cudaEventElapsedTime(&d, t_ev[4], t_ev[5]);
+        cudaEventElapsedTime(&f, t_ev[0], t_ev[5]);
+        fprintf(stderr, "[mapf timeline] h2d %.3f ms, step %.3f, observe %.3f, d2h copies %.3f (done %.3f after start)\n", a, b, c, d, f);
+    }
     return MAPF_OK;
 }
 

@@ -222,70 +222,100 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
             int head = 0, tail = __popc(qm), iters = 0;
             uint32_t draw = 0;
             __syncwarp();
+            // Every iteration is executed by the whole warp on warp-uniform values: the popped agent's masks arrive by
+            // shuffle, lanes 0..11 each look at one cell of its radius-2 diamond, two `redux.or` collect the conflict
+            // bits and the eviction set.  (One lane doing this alone made an iteration ~1.4 us of dependent
+            // instructions; a world in the reference's livelock runs FIX_CAP of them and was the tail of the launch.)
+            int tcur = (v.TL > 0) ? v.tape_cur[w] : 0;
+            const int tcur0 = tcur;
+            const uint32_t nstep_w = (uint32_t)v.nstep[w];
+            uint32_t pd = 0;                       // Philox draws [32*(draw/32), +32), one per lane, made when first needed
+            int pd_batch = -1;
             while (head < tail) {
                 if (++iters > FIX_CAP) { errbits |= MAPF_ERR_FIX_ITER_CAP; break; }
                 const int k = s.queue[(head++) & (QRING - 1)];
-                int new_tail = tail;
-                if (lane == k) {
-                    const uint32_t viable = ~(inv0 | inv1) & 31u;                 // :575
-                    uint32_t r2, c2, m2;
-                    scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, -1, r2, c2, m2);
-                    const uint32_t ok = viable & ~(restr & c2);                   // :577-584
-                    int choice;
-                    if (good) {
-                        choice = __ffs(good) - 1;                                 // an evicted agent may own a good action (:568)
-                    } else if (ok) {
+                const uint32_t kgood = __shfl_sync(FULL, good, k);
+                int choice;
+                if (kgood) {
+                    choice = __ffs(kgood) - 1;                                    // an evicted agent may own a good action (:568)
+                } else {
+                    const uint32_t viable = ~__shfl_sync(FULL, inv0 | inv1, k) & 31u;      // :575
+                    const uint32_t krestr = __shfl_sync(FULL, restr, k);
+                    const int kgr = __shfl_sync(FULL, gr, k), kgc = __shfl_sync(FULL, gc, k);
+                    uint32_t myc = 0;                                             // bit a: conflict(k, a; my cell's agent, its commit)
+                    int myj = 0;
+                    if (lane < 12) {
+                        const int dr = (int)((0x433322221110ull >> (4 * lane)) & 15) - 2;
+                        const int dc = (int)((0x232143103212ull >> (4 * lane)) & 15) - 2;
+                        const int code = s.grid[(kgr + dr) * GS + (kgc + dc)];
+                        if (code != 0 && code != k + 1) {
+                            myj = code - 1;
+                            const int b = s.commit[myj];
+                            const int tr = dr + (b >= 0 ? dr_of(b) : 0), tc = dc + (b >= 0 ? dc_of(b) : 0);   // T_j - pos_k
+#pragma unroll
+                            for (int a2 = 0; a2 < NA; ++a2) {
+                                const int ar = (a2 == 2) - (a2 == 4), ac = (a2 == 1) - (a2 == 3);
+                                bool cf = (b >= 0) && (tr == ar) && (tc == ac);                                      // vertex
+                                if (a2 != 0 && dr == ar && dc == ac) cf = cf || (b == (a2 == 1 ? 3 : a2 == 2 ? 4 : a2 == 3 ? 1 : 2));  // swap
+                                if (cf) myc |= 1u << a2;
+                            }
+                        }
+                    }
+                    const uint32_t c2 = __reduce_or_sync(FULL, myc);
+                    const uint32_t ok = viable & ~(krestr & c2);                  // :577-584
+                    if (ok) {
                         choice = __ffs(ok) - 1;
                     } else if (!viable) {
                         errbits |= MAPF_ERR_NO_VIABLE;                            // reference: IndexError (:588)
                         choice = 0;
                     } else {
                         const int nv = __popc(viable);
-                        uint32_t ev = 0;
                         if (v.TL > 0) {                                           // recorded random.choice + eviction order
                             const int8_t *tp = v.tape + (size_t)w * v.TL;
-                            int cur = v.tape_cur[w];
                             const int tl = v.tape_len[w];
-                            if (cur + 2 > tl) { errbits |= MAPF_ERR_TAPE; choice = __ffs(viable) - 1; cur = tl; }
+                            if (tcur + 2 > tl) { errbits |= MAPF_ERR_TAPE; choice = __ffs(viable) - 1; tcur = tl; }
                             else {
-                                choice = tp[cur];
-                                const int ne = tp[cur + 1];
+                                choice = tp[tcur];
+                                const int ne = tp[tcur + 1];
                                 if (choice < 0 || choice >= NA) { errbits |= MAPF_ERR_TAPE; choice = __ffs(viable) - 1; }
-                                scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
+                                const uint32_t ev = __reduce_or_sync(FULL, ((myc >> choice) & 1u) ? (1u << myj) : 0u);
                                 uint32_t seen = 0;
-                                for (int q = 0; q < ne && cur + 2 + q < tl; ++q) {
-                                    const int j = tp[cur + 2 + q];
+                                for (int q = 0; q < ne && tcur + 2 + q < tl; ++q) {
+                                    const int j = tp[tcur + 2 + q];
                                     if (j >= 0 && j < N && (ev >> j & 1)) {
                                         seen |= 1u << j;
-                                        s.commit[j] = -1;
-                                        s.queue[(new_tail++) & (QRING - 1)] = (int8_t)j;
+                                        if (lane == 0) { s.commit[j] = -1; s.queue[tail & (QRING - 1)] = (int8_t)j; }
+                                        tail++;
                                     }
                                 }
                                 if (seen != ev || __popc(ev) != ne) errbits |= MAPF_ERR_TAPE;
-                                ev = 0;
-                                cur += 2 + ne;
+                                tcur += 2 + ne;
                             }
-                            v.tape_cur[w] = cur;
                         } else {                                                  // Philox stand-in, ascending eviction
-                            int pick = (int)(philox_draw(v.seed, (uint32_t)(w + v.world_offset), (uint32_t)v.nstep[w], draw) % (uint32_t)nv);
+                            if ((int)(draw >> 5) != pd_batch) {                   // 32 draws cost the latency of one
+                                pd_batch = (int)(draw >> 5);
+                                pd = philox_draw(v.seed, (uint32_t)(w + v.world_offset), nstep_w, (draw & ~31u) + lane);
+                            }
+                            const uint32_t x = __shfl_sync(FULL, pd, draw & 31);
+                            // x % nv, nv in 1..5 (constant divisors: a multiply-high instead of a division loop)
+                            int pick = nv == 1 ? 0 : nv == 2 ? (int)(x & 1u) : nv == 3 ? (int)(x % 3u) : nv == 4 ? (int)(x & 3u) : (int)(x % 5u);
                             uint32_t vm = viable;
                             while (pick--) vm &= vm - 1;
                             choice = __ffs(vm) - 1;
-                            scan_diamond<false>(s.grid, GS, gr, gc, lane + 1, s.commit, choice, r2, c2, ev);
+                            uint32_t ev = __reduce_or_sync(FULL, ((myc >> choice) & 1u) ? (1u << myj) : 0u);
+                            while (ev) {                                          // :593-596
+                                const int j = __ffs(ev) - 1; ev &= ev - 1;
+                                if (lane == 0) { s.commit[j] = -1; s.queue[tail & (QRING - 1)] = (int8_t)j; }
+                                tail++;
+                            }
                         }
                         draw++;
-                        while (ev) {                                              // :593-596
-                            const int j = __ffs(ev) - 1; ev &= ev - 1;
-                            s.commit[j] = -1;
-                            s.queue[(new_tail++) & (QRING - 1)] = (int8_t)j;
-                        }
                     }
-                    s.commit[lane] = (int8_t)choice;                              // :598
                 }
-                tail = __shfl_sync(FULL, new_tail, k);
-                draw = __shfl_sync(FULL, draw, k);
+                if (lane == 0) s.commit[k] = (int8_t)choice;                      // :598
                 __syncwarp();
             }
+            if (v.TL > 0 && lane == 0 && tcur != tcur0) v.tape_cur[w] = tcur;
         }
         __syncwarp();
         if (active) { f = s.commit[lane]; if (f < 0) f = 0; }
