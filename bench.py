@@ -10,8 +10,9 @@ uniform random actions.  Weak scaling: every rank owns 65 536 worlds; worlds nev
 
 Printed JSON (rank 0): value = whole-job agent-steps/s with inputs resident in HBM; `e2e` = the same through the
 host-buffer C-ABI call (actions from pinned host memory, per-agent results read back to the host every step);
-`roofline` for the dominant kernel (observe) from CUDA events inside the timed region; `cpu_baseline` = the C port
+`roofline` for the dominant kernel (the fused step_observe_kernel) from CUDA events inside the timed region; `cpu_baseline` = the C port
 of the reference's algorithm (oracle/) on this box's host cores.  `--impl reference` times that CPU path alone.
+BENCH_E2E_DEBUG=1 prints the wall time of every e2e call on stderr.
 """
 from __future__ import annotations
 
