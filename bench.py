@@ -393,6 +393,25 @@ def main():
         line_extra["bfs"] = {"maps": nb * N, "ms": bfs_ms, "maps_per_s": nb * N / (bfs_ms * 1e-3),
                              "achieved_gbs": bfs_bytes / (bfs_ms * 1e-3) / 1e9, "frac": bfs_bytes / (bfs_ms * 1e-3) / 1e9 / peak}
         del bfs_out
+        # BFS "all W*N maps" (reset-time) and "arrivals only" (in-loop mapf_bfs_refresh after a step)
+        try:
+            maps = env.bfs_maps()                                   # [W, N, H, Wd] int16
+            torch.cuda.synchronize(dev)
+            a.record(); env.bfs_maps(out=maps); b.record(); torch.cuda.synchronize(dev)
+            all_ms = a.elapsed_time(b)
+            evr = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(10)]
+            arrived = torch.zeros((), dtype=torch.int64, device=dev)
+            for i in range(10):
+                so = env.step(ring[i % 8])
+                arrived += so.goals_reached.sum()
+                evr[i][0].record(); env.refresh_bfs(maps); evr[i][1].record()
+            torch.cuda.synchronize(dev)
+            line_extra["bfs_all_and_refresh"] = {"all_maps": Wn * N, "all_maps_ms": all_ms,
+                                                 "refresh_ms_per_step": float(np.mean([x.elapsed_time(y) for x, y in evr])),
+                                                 "arrivals_per_step": float(arrived.item()) / 10}
+            del maps
+        except Exception as ex:
+            line_extra["bfs_all_and_refresh"] = {"error": str(ex)[:200]}
         T, cols = 256, 8192 * N
         r = torch.randn((T, cols), device=dev); v = torch.randn((T, cols), device=dev); lv = torch.randn((cols,), device=dev)
         gae(r, v, lv); torch.cuda.synchronize(dev)
