@@ -354,6 +354,54 @@ def test_gpu_bfs_deep_mazes():
     _eq(_np(env.bfs_maps(agent_ids=ids)), ref.reshape(W * N, H, H)[ids.cpu().numpy()], "listed maps")
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_gpu_fix_actions_livelock_world(fused):
+    """The reference's `while problemAgents` loop (mapf_gym.py:563) never ends for two boxed-in agents whose only
+    viable actions collide: A at (1,1) can only move right (its stay is the human's next cell, its move down a swap
+    with the human), B at (1,2) can only stay (its move left is the human's next cell).  Both implementations stop
+    after the same number of iterations, flag the world with MAPF_ERR_FIX_ITER_CAP and leave identical state and
+    outputs — compared here for EVERY world, the flagged one included."""
+    from primal_ppo_b200.scenario import Scenario, looping_trace
+    W, H, N = 4, 8, 2
+    base = random_scenario(W, H, H, N, density=(0.0, 0.2), queue_len=3, seed=9)
+    obst = base.obst.copy(); starts = base.starts.copy(); queue = base.goal_queue.copy()
+    htrace = base.htrace.copy(); hlen = base.hlen.copy()
+    m = np.ones((H, H), dtype=np.uint8)
+    m[1, 1] = 0; m[1, 2] = 0; m[2, 1] = 0
+    obst[0] = m
+    starts[0, 0] = (1, 1); starts[0, 1] = (1, 2)
+    queue[0, 0, :] = (2, 1); queue[0, 1, :] = (1, 1)
+    tr = looping_trace([(2, 1), (1, 1), (2, 1)])
+    htrace[0, :len(tr)] = tr; htrace[0, len(tr):] = tr[-1]; hlen[0] = len(tr)
+    sc = Scenario(obst=obst, starts=starts, goal_queue=queue, htrace=htrace, hlen=hlen)
+    sc.validate()
+    orc = OracleMapfGym(sc, seed=1234, threads=2, use_tape=False)
+    env = _env(sc, seed=1234, use_tape=False)
+    rng = np.random.default_rng(3)
+    for t in range(4):
+        acts = rng.integers(0, 5, size=(W, N)).astype(np.int8)
+        if t % 2 == 0:
+            acts[0] = (1, 0)                                   # A right, B stay: vertex conflict -> fixActions
+        ref = orc.step(acts)
+        if fused:
+            out, obs, vec = env.step_observe(torch.from_numpy(acts))
+        else:
+            out = env.step(torch.from_numpy(acts))
+            obs, vec = env.getAllObservations()
+        e_ref = orc.state()["err"]
+        np.testing.assert_array_equal(_np(env.state()["err"]).astype(np.uint32), e_ref, err_msg=f"t={t} err flags")
+        if t == 0:
+            assert e_ref[0] & 2 and not e_ref[1:].any()        # MAPF_ERR_FIX_ITER_CAP on the livelock world only
+        for key in ("status", "reward", "cost", "train_valid", "goals_reached", "violated"):
+            _eq(_np(getattr(out, key)), ref[key], f"t={t} {key}")
+        _eq(_np(out.fixed_actions), ref["fixed"], f"t={t} fixed")
+        s, so = env.state(), orc.state()
+        for key in ("pos", "goal", "rep"):
+            _eq(_np(s[key]), so[key], f"t={t} {key}")
+        o_obs, o_vec = orc.getAllObservations()
+        assert torch.equal(obs, torch.from_numpy(o_obs).cuda()) and torch.equal(vec, torch.from_numpy(o_vec).cuda()), f"t={t} obs"
+
+
 @pytest.mark.parametrize("shape", [(8, 5), (8, 8), (6, 12), (16, 31), (8, 32), (24, 33), (40, 40), (17, 40), (12, 64),
                                    (9, 96), (30, 100), (8, 127), (25, 128), (64, 64), (100, 72), (7, 9), (11, 13)])
 def test_gpu_bfs_map_shapes(shape):
