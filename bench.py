@@ -345,7 +345,7 @@ def main():
     obs_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evk]))
 
     # ---------------- end to end through the host-buffer C-ABI call ---------------------------------------------
-    Ke = max(3, min(K, 20))
+    Ke = max(3, min(K, 50))
     e2e_s, h2d, d2h = run_e2e(Ke)
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world_size > 1:
