@@ -12,7 +12,13 @@
  *  - Actions 0..4 = stay, (0,+1), (+1,0), (0,-1), (-1,0)                      (mapf_gym.py:97-98)
  *  - Unless a function name ends in `_host`, every data pointer is a DEVICE pointer on the env's device
  *    and the call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
- *    No allocation and no host synchronisation happens inside reset/evaluate/step/observe/bfs/gae.
+ *    No allocation and no host synchronisation happens inside reset/evaluate/step/observe/bfs/gae (the staging of the
+ *    *_host entry points is allocated by mapf_create).
+ *  - Alignment: vec and the scenario's starts / goal_queue must be 4-byte aligned per (row, col) pair and vec 16-byte
+ *    aligned; htrace 8-byte aligned; obs 4-byte (16-byte aligned buffers take the vector-store path).
+ *  - A handle is single-stream: calls on one MapfEnv must be issued from one thread and are ordered on the streams
+ *    passed; two calls of the same env must not run concurrently on different streams (every kernel family has its own
+ *    work counter, re-armed by mapf_reset, but the env state itself is not versioned).
  *  - The caller owns every input/output buffer.  Scenario arrays passed to mapf_reset are BORROWED and
  *    must stay alive and unchanged until the next mapf_reset / mapf_destroy.
  *  - Return value: 0 on success, a negative MAPF_E_* code otherwise; mapf_last_error() gives the text.
@@ -27,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MAPF_B200_ABI_VERSION 1
+#define MAPF_B200_ABI_VERSION 2
 
 /* return codes */
 #define MAPF_OK 0
@@ -42,6 +48,7 @@ extern "C" {
 #define MAPF_ERR_FIX_ITER_CAP 2u /* livelock of the fixActions while loop     mapf_gym.py:563 */
 #define MAPF_ERR_BAD_ACTION 4u   /* action outside 0..4                       mapf_gym.py:452-456 */
 #define MAPF_ERR_TAPE 8u         /* fixActions tape exhausted / inconsistent */
+#define MAPF_ERR_NO_FREE_CELL 64u /* goal_sampling: no free cell found in 4096 draws (getFreeCell would spin for ever, util.py:72) */
 
 typedef struct MapfEnv MapfEnv; /* opaque; one handle per (process, device); not thread-safe */
 
@@ -64,6 +71,14 @@ typedef struct MapfConfig {
     int32_t device;       /* CUDA device ordinal */
     int32_t world_offset; /* global index of this env's world 0 (rank r of a sharded job: r*W): keys the Philox draws so
                              that world w behaves identically on whichever rank owns it */
+    int32_t goal_sampling;/* 0: goals come from goal_queue (FixedMapfGym.getNextGoal, mapf_gym.py:668-669: Sequence.getNext);
+                             1: on arrival the next goal is drawn ON DEVICE like MapfGym.getNextGoal (mapf_gym.py:189-190,
+                                626) = util.getFreeCell (util.py:67-76) on worldWithAgentsAndGoals(): uniform rejection
+                                sampling over cells free of obstacles, of every agent's cell (agents before the arriving one
+                                already moved, the others not yet) and of every current goal.  Philox4x32-10 keyed by
+                                (seed; world_offset + w, step, draw): the reference's distribution, not its MT19937 bits.
+                                goal_queue[:, :, 0] still supplies the first goal. */
+    int32_t reserved0;
 } MapfConfig;
 
 /* Exogenous inputs of a batch of worlds — what the reference draws from np.random / random at construction and on
@@ -90,6 +105,9 @@ typedef struct MapfStepOut {
     uint8_t *violated;     /* [W,N]   jointStep()[1] */
     int32_t *shadow_goals; /* [W]     calculateActionReward()[1] */
     int8_t *fixed_actions; /* [W,N]   the actions actually executed (after fixActions, mapf_gym.py:552-612) */
+    uint8_t *good_actions; /* [W,N]   MapfGym.allGoodActions (mapf_gym.py:404-430, refreshed at :169/:635) as 5-bit masks, bit a =
+                              action a is unconditionally good in the CURRENT state; written by mapf_evaluate only (the
+                              masks do not depend on the actions passed) */
 } MapfStepOut;
 
 int mapf_abi_version(void);
@@ -158,6 +176,10 @@ int mapf_sample_actions(const float *ps, int64_t rows, uint64_t seed, uint32_t d
  * pos/goal int16 [W,N,2], rep int8 [W,N] (the repetition action or -1, mapf_gym.py:161), err u32 [W]. */
 int mapf_get_state(MapfEnv *env, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream);
 
+/* The human walker of every world (Human.getPos / getNextPos / step, mapf_gym.py:25-50; device pointers, any may be
+ * NULL): pos_next int16 [W,4] = (pos_r, pos_c, next_r, next_c) of the current tick, tick int32 [W]. */
+int mapf_get_human(MapfEnv *env, int16_t *pos_next, int32_t *tick, void *stream);
+
 /* Checkpoint / resume of everything reset and step mutate (cells, goals, repetition actions, queue cursors, human tick,
  * tape cursor, step count, error flags, episode counters) as one opaque device blob of mapf_state_bytes() bytes.  The
  * scenario arrays are not part of it (they are borrowed and immutable): a blob is valid for an env created with the same
@@ -208,16 +230,53 @@ int mapf_generate_scenario(const MapfGenConfig *cfg, uint8_t *obst /*[W,H,Wd]*/,
  * slower than slices of a single slab). */
 typedef struct MapfStepOutHost {
     int8_t *status; float *reward; float *cost; float *train_valid; uint8_t *goals_reached; uint8_t *violated;
-    int32_t *shadow_goals; int8_t *fixed_actions;
+    int32_t *shadow_goals; int8_t *fixed_actions; uint8_t *good_actions /* ignored */;
 } MapfStepOutHost;
 
-/* actions_host -> device, mapf_step, mapf_observe into obs_dev/vec_dev (device; the policy's input tensors),
- * step outputs -> host, stream synchronised before return.  train_valid_dev (device, optional) receives trainValid
- * [W,N,5] in HBM — like the observations it is training data that the learner consumes on the GPU; it is copied to the
- * host only if out->train_valid is non-NULL.  If obs_host / vec_host are non-NULL the observations are also copied to
- * the host (what the reference's getAllObservations returns). */
+/* SYNCHRONOUS form.  actions_host -> device, mapf_step, mapf_observe into obs_dev/vec_dev (device; the policy's input
+ * tensors), step outputs -> host (copied on the env's copy stream while the observation kernel runs), stream
+ * synchronised before return.  train_valid_dev (device, optional) receives trainValid [W,N,5] in HBM — like the
+ * observations it is training data that the learner consumes on the GPU; out->train_valid (host) needs it.  If obs_host /
+ * vec_host are non-NULL the observations are also copied to the host (what the reference's getAllObservations returns). */
 int mapf_step_observe_host(MapfEnv *env, const int8_t *actions_host, const MapfStepOutHost *out, float *obs_dev,
                            float *vec_dev, float *train_valid_dev, float *obs_host, float *vec_host, void *stream);
+
+/* SPLIT-PHASE form (what a rollout loop should use): nothing in runner.py:64-100 needs the rewards / status of step t
+ * before step t+1 starts (they are appended to the rollout lists, runner.py:84-99), so the results of step t travel to the
+ * host while step t+1 computes.
+ *
+ * All per-agent results of one step live in ONE contiguous "result slot" whose layout mapf_host_layout reports (same
+ * layout on the device and on the host; every field 256-byte aligned):
+ *   reward f32[W,N] | cost f32[W,N] | shadow_goals i32[W] | status i8[W,N] | goals_reached u8[W,N] | violated u8[W,N] |
+ *   fixed_actions i8[W,N] | (train_valid f32[W,N,5] when with_train_valid)
+ * mapf_step_observe_host_begin: actions_host -> device (own copy stream, double-buffered), ONE fused step+observe launch
+ * on `stream` writing obs_dev / vec_dev (and train_valid_dev if given) and the env's device slot, then ONE device-to-host
+ * copy of the slot into result_slot_host on the copy stream.  Returns without any host synchronisation: work queued on
+ * `stream` afterwards (the policy forward) sees obs_dev / vec_dev of this step.  The env keeps two device slots, so two
+ * begins may be in flight; result_slot_host must stay untouched until the matching wait.
+ * mapf_step_observe_host_wait(env, age): block the host until the results of the most recent begin (age 0) or of the one
+ * before it (age 1) have landed in their result_slot_host.
+ * with_train_valid != 0 needs train_valid_dev and makes the next begin wait for this step's copy (the caller's
+ * trainValid tensor is the copy source). */
+typedef struct MapfHostLayout {
+    int64_t slot_bytes; /* bytes of one result slot (with_train_valid as passed to mapf_host_layout) */
+    int64_t off_reward, off_cost, off_shadow_goals, off_status, off_goals_reached, off_violated, off_fixed_actions,
+        off_train_valid; /* -1 when absent */
+} MapfHostLayout;
+int mapf_host_layout(MapfEnv *env, int with_train_valid, MapfHostLayout *out);
+int mapf_step_observe_host_begin(MapfEnv *env, const int8_t *actions_host, void *result_slot_host, int with_train_valid,
+                                 float *obs_dev, float *vec_dev, float *train_valid_dev, void *stream);
+int mapf_step_observe_host_wait(MapfEnv *env, int age);
+
+/* ---- integrity helper ------------------------------------------------------------------------------------------------- */
+
+/* 64-bit checksum of every row of a [rows, row_bytes] device array (row_bytes a multiple of 4, data 4-byte aligned):
+ *   out[r] = sum over 32-bit words i of mix64((uint64(x[r,i]) + 1) * 0x9E3779B97F4A7C15 + i * 0xC2B2AE3D27D4EB4F)   (mod 2^64),
+ *   mix64(z) = (z ^ (z >> 29)) * 0xBF58476D1CE4E5B9, then z ^ (z >> 32).
+ * Order-independent sum of position-keyed terms, so a 4 GB observation tensor is verified against another implementation
+ * (the reference's arrays, hashed the same way on the host) without moving it: compare W 64-bit values.  The reference
+ * has no counterpart. */
+int mapf_checksum_rows(const void *data, int64_t rows, int64_t row_bytes, uint64_t *out, void *stream);
 
 #ifdef __cplusplus
 }

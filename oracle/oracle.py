@@ -71,6 +71,8 @@ def _load():
         lib.orc_gae.argtypes = [p, p, p, C.c_double, C.c_double, C.c_int, C.c_int, p, p]
         lib.orc_sample_actions.argtypes = [p, C.c_longlong, C.c_uint64, C.c_uint32, p, p]
         lib.orc_max_threads.restype = C.c_int
+        lib.orc_set_goal_sampling.argtypes = [p, C.c_int]
+        lib.orc_checksum_rows.argtypes = [p, C.c_longlong, C.c_longlong, p, C.c_int]
         _lib = lib
     return _lib
 
@@ -82,7 +84,8 @@ def _ptr(a):
 class OracleMapfGym:
     """Batched CPU oracle with the reference's method surface (leading world dim W)."""
 
-    def __init__(self, scenario, seed: int = 1234, threads: int = 1, use_tape: bool = True, world_offset: int = 0):
+    def __init__(self, scenario, seed: int = 1234, threads: int = 1, use_tape: bool = True, world_offset: int = 0,
+                 goal_sampling: bool = False):
         lib = _load()
         sc = scenario
         sc.validate()
@@ -99,6 +102,8 @@ class OracleMapfGym:
                                  int(sc.hp5 is not None and sc.hp5.ndim == 4), _ptr(self._keep[6]), _ptr(self._keep[7]),
                                  TL, _ptr(self._dims), C.c_uint64(seed), int(threads), int(world_offset))
         self._lib = lib
+        self.threads = int(threads)
+        lib.orc_set_goal_sampling(self._h, int(bool(goal_sampling)))
         lib.orc_reset(self._h)
 
     def __del__(self):
@@ -224,6 +229,20 @@ def sample_actions_oracle(ps, seed=1234, draw=0):
     cp = np.empty(p.shape[:-1], dtype=np.float32)
     lib.orc_sample_actions(_ptr(p), rows, int(seed) & (2 ** 64 - 1), int(draw) & 0xffffffff, _ptr(a), _ptr(cp))
     return a, cp
+
+
+def checksum_rows(a: np.ndarray, threads: int = 1) -> np.ndarray:
+    """Row checksums with the definition of ``mapf_checksum_rows`` (include/mapf_b200.h): a [rows, ...] array of 4-byte
+    items -> uint64 [rows]."""
+    lib = _load()
+    a = np.ascontiguousarray(a)
+    rows = a.shape[0]
+    words = (a.size // max(rows, 1)) * a.itemsize // 4 if rows else 0
+    assert a.itemsize * (a.size // max(rows, 1)) % 4 == 0
+    out = np.empty((rows,), dtype=np.uint64)
+    if rows:
+        lib.orc_checksum_rows(_ptr(a), rows, words, _ptr(out), int(threads))
+    return out
 
 
 def max_threads() -> int:

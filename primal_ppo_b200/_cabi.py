@@ -14,16 +14,19 @@ EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy"
             "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae",
             "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe",
             "mapf_sample_actions", "mapf_generate_scenario",
-            "mapf_observe_bf16", "mapf_step_observe_bf16", "mapf_state_bytes", "mapf_save_state", "mapf_load_state"]
+            "mapf_observe_bf16", "mapf_step_observe_bf16", "mapf_state_bytes", "mapf_save_state", "mapf_load_state",
+            "mapf_get_human", "mapf_host_layout", "mapf_step_observe_host_begin", "mapf_step_observe_host_wait", "mapf_checksum_rows"]
+ABI_VERSION = 2
 
-ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE = 1, 2, 4, 8
+ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE, ERR_NO_FREE_CELL = 1, 2, 4, 8, 64
 
 
 class MapfConfig(C.Structure):
     _fields_ = [("num_worlds", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("num_agents", C.c_int32),
                 ("fov", C.c_int32), ("num_channel", C.c_int32), ("use_da", C.c_int32), ("use_hp", C.c_int32),
                 ("queue_len", C.c_int32), ("trace_len", C.c_int32), ("tape_stride", C.c_int32),
-                ("hp5_per_tick", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("world_offset", C.c_int32)]
+                ("hp5_per_tick", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("world_offset", C.c_int32),
+                ("goal_sampling", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class MapfGenConfig(C.Structure):
@@ -41,10 +44,16 @@ class MapfScenario(C.Structure):
 class MapfStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals",
-                 "fixed_actions")]
+                 "fixed_actions", "good_actions")]
 
 
 MapfStepOutHost = MapfStepOut   # same layout, host pointers
+
+
+class MapfHostLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in
+                ("slot_bytes", "off_reward", "off_cost", "off_shadow_goals", "off_status", "off_goals_reached",
+                 "off_violated", "off_fixed_actions", "off_train_valid")]
 
 
 class MapfError(RuntimeError):
@@ -86,7 +95,12 @@ def load_library():
     lib.mapf_load_state.argtypes = [vp, vp, vp]
     lib.mapf_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.mapf_get_counters.argtypes = [vp, vp, vp]
+    lib.mapf_get_human.argtypes = [vp, vp, vp, vp]
     lib.mapf_step_observe_host.argtypes = [vp, vp, C.POINTER(MapfStepOutHost), vp, vp, vp, vp, vp, vp]
+    lib.mapf_host_layout.argtypes = [vp, C.c_int, C.POINTER(MapfHostLayout)]
+    lib.mapf_step_observe_host_begin.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.mapf_step_observe_host_wait.argtypes = [vp, C.c_int]
+    lib.mapf_checksum_rows.argtypes = [vp, i64, i64, vp, vp]
     for n in EXPORTED:
         if n not in ("mapf_last_error",):
             getattr(lib, n).restype = C.c_int

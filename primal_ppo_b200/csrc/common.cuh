@@ -38,6 +38,7 @@ struct EnvView {
     int GS;       // byte stride of one row of the shared-memory agent-id grid (multiple of 16)
     int dbg_flags; // experiment switches (MAPF_DBG_FLAGS), 0 in production
     int world_offset; // global index of world 0 (sharded jobs): Philox counter = world_offset + w
+    int goal_sampling; // 1: draw the next goal on device at arrival (MapfGym.getNextGoal) instead of popping goal_queue
     unsigned long long seed;
     // borrowed scenario
     const uint8_t *obst;
@@ -111,6 +112,32 @@ __device__ __forceinline__ uint32_t philox_draw(unsigned long long seed, uint32_
     }
     return c0;
 }
+
+// All four words of the same generator with a caller-chosen tag in counter word 3: the free-cell draws of on-device
+// goal sampling (tag "GOAL") use words 0 and 1 for (row, col).  Bit-identical to the oracle's philox4.
+constexpr uint32_t PHILOX_TAG_GOAL = 0x474F414Cu;
+__device__ __forceinline__ void philox4(unsigned long long seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                        uint32_t &o0, uint32_t &o1) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1;
+}
+// candidate cell of free-cell draw `d` (util.getFreeCell, util.py:72-74: two independent uniform integers), packed like pos
+__device__ __forceinline__ uint32_t goal_candidate(unsigned long long seed, uint32_t world, uint32_t step, uint32_t d,
+                                                   int rows, int cols) {
+    uint32_t x0, x1;
+    philox4(seed, world, step, d, PHILOX_TAG_GOAL, x0, x1);
+    const uint32_t r = __umulhi(x0, (uint32_t)rows), c = __umulhi(x1, (uint32_t)cols);
+    return r | (c << 16);
+}
+constexpr int GOAL_DRAW_CAP = 4096;   // draws per arrival before MAPF_ERR_NO_FREE_CELL (the reference would spin for ever)
 
 // L2 residency hints.  The env state (cells, goals, obstacle bit rows, human tick: ~55 MB for 65 536 worlds) is re-read
 // every step while 4 GB of observations stream through the same L2.  DRAM reads interleaved with the write stream cost
@@ -222,6 +249,8 @@ cudaError_t launch_gae(const float *r, const float *v, const float *last_v, cons
 
 cudaError_t launch_sample_actions(const float *ps, long long rows, unsigned long long seed, uint32_t draw, int8_t *actions,
                                   float *chosen_p, cudaStream_t s);
+
+cudaError_t launch_checksum_rows(const uint32_t *data, long long rows, long long words, unsigned long long *out, cudaStream_t s);
 
 cudaError_t launch_scenario_gen(const MapfGenConfig &c, uint8_t *obst, int16_t *dims, int16_t *starts, int16_t *goal_queue,
                                 int16_t *htrace, int32_t *hlen, int16_t *hp5, uint32_t *gen_err, cudaStream_t s);

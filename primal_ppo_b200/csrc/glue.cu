@@ -40,7 +40,51 @@ __global__ void __launch_bounds__(256) sample_actions_kernel(const float *__rest
     }
 }
 
+// checksum_rows_kernel: 64-bit position-keyed checksum of every row of a [rows, words] u32 array (mapf_checksum_rows).
+// One CTA per row at a time (grid-stride over rows), 16-byte loads when the row allows, order-independent sum.
+__device__ __forceinline__ unsigned long long mix_word(uint32_t x, unsigned long long i) {
+    unsigned long long z = ((unsigned long long)x + 1ull) * 0x9E3779B97F4A7C15ull + i * 0xC2B2AE3D27D4EB4Full;
+    z = (z ^ (z >> 29)) * 0xBF58476D1CE4E5B9ull;
+    return z ^ (z >> 32);
+}
+
+__global__ void __launch_bounds__(256) checksum_rows_kernel(const uint32_t *__restrict__ data, const long long rows,
+                                                            const long long words, unsigned long long *__restrict__ out) {
+    __shared__ unsigned long long part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const uint32_t *row = data + r * words;
+        unsigned long long acc = 0;
+        if (((reinterpret_cast<uintptr_t>(row) & 15) == 0) && (words & 3) == 0) {
+            const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+            for (long long q = threadIdx.x; q < (words >> 2); q += blockDim.x) {
+                const uint4 x = __ldcs(row4 + q);
+                acc += mix_word(x.x, 4 * q) + mix_word(x.y, 4 * q + 1) + mix_word(x.z, 4 * q + 2) + mix_word(x.w, 4 * q + 3);
+            }
+        } else {
+            for (long long i = threadIdx.x; i < words; i += blockDim.x) acc += mix_word(__ldcs(row + i), i);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += part[k];
+            out[r] = t;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_checksum_rows(const uint32_t *data, long long rows, long long words, unsigned long long *out, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const int blocks = (int)(rows < 148 * 8 ? rows : 148 * 8);
+    checksum_rows_kernel<<<blocks, 256, 0, s>>>(data, rows, words, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_sample_actions(const float *ps, long long rows, unsigned long long seed, uint32_t draw, int8_t *actions,
                                   float *chosen_p, cudaStream_t s) {

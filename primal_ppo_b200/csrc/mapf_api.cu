@@ -9,21 +9,27 @@
 
 using namespace mapf;
 
+// work counters (2 ints each) of the persistent kernels: one per kernel family, so that a launch that aborted, or two
+// families in flight on different streams, can never hand a stale counter to another kernel
+enum { WC_STEP = 0, WC_OBSERVE = 1, WC_FUSED = 2, WC_BFS = 3, WC_FUSED_WIDE = 4, WC_COUNT = 8 };
+
 struct MapfEnv {
     MapfConfig cfg;
     EnvView v;
     bool has_scenario;
-    // staging for the *_host entry points (allocated on first use)
-    int8_t *d_actions;
-    MapfStepOut d_out;
-    bool staging;
     // arrivals compaction scratch for mapf_bfs_refresh
     int32_t *d_list, *d_count;
-    int *d_work;   // dynamic-scheduling counter of step_kernel / observe_kernel
-    int *d_work_bfs;
-    // mapf_step_observe_host: the step results travel to the host on their own stream while observe_kernel runs
-    cudaStream_t copy_stream;
-    cudaEvent_t ev_step, ev_copied;
+    int *d_work;   // [WC_COUNT][2] dynamic-scheduling counters
+    // ---- staging of the *_host entry points (allocated by mapf_create) --------------------------------------------------
+    // two result slots (layout: MapfHostLayout without train_valid) and two action buffers, used alternately
+    unsigned char *d_slot[2];
+    int8_t *d_actions[2];
+    MapfHostLayout lay;                      // layout of a slot (no train_valid)
+    cudaStream_t copy_stream, h2d_stream;
+    cudaEvent_t ev_step[2], ev_copied[2], ev_h2d[2];
+    bool tv_copy_pending[2];                 // that begin also copied the caller's trainValid tensor
+    int next_slot;                           // slot the next begin uses; the most recent begin used next_slot ^ 1
+    int begun;                               // number of begins so far (saturating at 2)
 };
 
 static thread_local char g_err[512] = "";
@@ -91,6 +97,22 @@ cudaError_t launch_reset(const EnvView &v, cudaStream_t s) {
 }
 }  // namespace mapf
 
+// Every entry point runs on the env's device whatever the caller's current device is, and leaves the caller's current
+// device as it found it (a process that drives several GPUs from one thread keeps its own notion of "current").
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = err == cudaSuccess; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                \
+    DeviceGuard dev_guard_(dev);      \
+    if (dev_guard_.err != cudaSuccess) return cuda_fail(dev_guard_.err, "cudaSetDevice")
+
 extern "C" {
 
 int mapf_abi_version(void) { return MAPF_B200_ABI_VERSION; }
@@ -107,7 +129,7 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
     if (c.fov < 3 || c.fov > 31 || (c.fov & 1) == 0) return fail(MAPF_E_BAD_CONFIG, "mapf_create: fov must be odd in 3..31");
     if (c.num_channel != 5 && c.num_channel != 6) return fail(MAPF_E_BAD_CONFIG, "mapf_create: num_channel must be 5 or 6");
     if (c.queue_len < 1 || c.trace_len < 1 || c.tape_stride < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_create: bad Q / L / TL");
-    CU(cudaSetDevice(c.device));
+    ON_DEVICE(c.device);
     MapfEnv *e = new (std::nothrow) MapfEnv();
     if (!e) return fail(MAPF_E_CUDA, "mapf_create: out of host memory");
     memset(e, 0, sizeof(*e));
@@ -116,6 +138,7 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
     v.W = c.num_worlds; v.H = c.height; v.Wd = c.width; v.N = c.num_agents; v.F = c.fov; v.C = c.num_channel;
     v.use_da = c.use_da; v.use_hp = c.use_hp; v.Q = c.queue_len; v.L = c.trace_len; v.TL = c.tape_stride;
     v.hp5_per_tick = c.hp5_per_tick; v.seed = c.seed; v.world_offset = c.world_offset;
+    v.goal_sampling = c.goal_sampling ? 1 : 0;
     v.P = c.fov / 2 > 2 ? c.fov / 2 : 2;
     v.HP = v.H + 2 * v.P;
     v.RW = (v.Wd + 2 * v.P + 31) / 32 + 1;
@@ -136,13 +159,37 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
     alloc((void **)&v.counters, W * 6 * 8);
     alloc((void **)&v.hcur, W * 8);
     alloc((void **)&v.hnx, W * 8);
-    alloc((void **)&e->d_work, 8);
-    alloc((void **)&e->d_work_bfs, 8);
+    alloc((void **)&e->d_work, WC_COUNT * 2 * sizeof(int));
     alloc((void **)&e->d_list, WN * 4);
     alloc((void **)&e->d_count, 4);
-    if (err != cudaSuccess) { mapf_destroy(e); return cuda_fail(err, "mapf_create: cudaMalloc"); }
-    cudaMemset(e->d_work, 0, 8);
-    cudaMemset(e->d_work_bfs, 0, 8);
+    // result-slot layout: f32 fields first, then the byte fields; every field 256-byte aligned
+    {
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        MapfHostLayout &L = e->lay;
+        size_t o = 0;
+        L.off_reward = (int64_t)o; o += up(WN * 4);
+        L.off_cost = (int64_t)o; o += up(WN * 4);
+        L.off_shadow_goals = (int64_t)o; o += up(W * 4);
+        L.off_status = (int64_t)o; o += up(WN);
+        L.off_goals_reached = (int64_t)o; o += up(WN);
+        L.off_violated = (int64_t)o; o += up(WN);
+        L.off_fixed_actions = (int64_t)o; o += up(WN);
+        L.off_train_valid = -1;
+        L.slot_bytes = (int64_t)o;
+    }
+    for (int k = 0; k < 2; ++k) {
+        alloc((void **)&e->d_slot[k], (size_t)e->lay.slot_bytes);
+        alloc((void **)&e->d_actions[k], WN);
+    }
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && err == cudaSuccess; ++k) {
+        err = cudaEventCreateWithFlags(&e->ev_step[k], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_h2d[k], cudaEventDisableTiming);
+    }
+    if (err != cudaSuccess) { mapf_destroy(e); return cuda_fail(err, "mapf_create: allocation"); }
+    cudaMemset(e->d_work, 0, WC_COUNT * 2 * sizeof(int));
     if (const char *f = getenv("MAPF_DBG_FLAGS")) v.dbg_flags = atoi(f);
     *out = e;
     return MAPF_OK;
@@ -152,15 +199,16 @@ int mapf_destroy(MapfEnv *e) {
     if (!e) return MAPF_OK;
     EnvView &v = e->v;
     cudaFree(v.obst_pack); cudaFree(v.pos); cudaFree(v.goal); cudaFree(v.rep); cudaFree(v.qcur); cudaFree(v.htick);
-    cudaFree(v.tape_cur); cudaFree(v.nstep); cudaFree(v.err); cudaFree(v.counters); cudaFree(v.hcur); cudaFree(v.hnx); cudaFree(e->d_work); cudaFree(e->d_work_bfs); cudaFree(e->d_list); cudaFree(e->d_count);
-    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-    if (e->ev_step) cudaEventDestroy(e->ev_step);
-    if (e->ev_copied) cudaEventDestroy(e->ev_copied);
-    if (e->staging) {
-        cudaFree(e->d_actions); cudaFree(e->d_out.status); cudaFree(e->d_out.reward); cudaFree(e->d_out.cost);
-        cudaFree(e->d_out.train_valid); cudaFree(e->d_out.goals_reached); cudaFree(e->d_out.violated);
-        cudaFree(e->d_out.shadow_goals); cudaFree(e->d_out.fixed_actions);
+    cudaFree(v.tape_cur); cudaFree(v.nstep); cudaFree(v.err); cudaFree(v.counters); cudaFree(v.hcur); cudaFree(v.hnx);
+    cudaFree(e->d_work); cudaFree(e->d_list); cudaFree(e->d_count);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(e->d_slot[k]); cudaFree(e->d_actions[k]);
+        if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
+        if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]);
+        if (e->ev_h2d[k]) cudaEventDestroy(e->ev_h2d[k]);
     }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
     delete e;
     return MAPF_OK;
 }
@@ -174,7 +222,9 @@ int mapf_reset(MapfEnv *e, const MapfScenario *sc, void *stream) {
     EnvView &v = e->v;
     v.obst = sc->obst; v.starts = sc->starts; v.goal_queue = sc->goal_queue; v.htrace = sc->htrace; v.hlen = sc->hlen;
     v.hp5 = sc->hp5; v.tape = sc->tape; v.tape_len = sc->tape_len; v.dims = sc->dims;
-    CU(cudaSetDevice(e->cfg.device));
+    ON_DEVICE(e->cfg.device);
+    // re-arm every work counter: a launch that faulted or was aborted must not leave later launches without work
+    CU(cudaMemsetAsync(e->d_work, 0, WC_COUNT * 2 * sizeof(int), (cudaStream_t)stream));
     CU(launch_reset(v, (cudaStream_t)stream));
     e->has_scenario = true;
     return MAPF_OK;
@@ -182,7 +232,9 @@ int mapf_reset(MapfEnv *e, const MapfScenario *sc, void *stream) {
 
 #define NEED_ENV(name)                                                                     \
     if (!e) return fail(MAPF_E_NULL, name ": null env");                                   \
-    if (!e->has_scenario) return fail(MAPF_E_STATE, name ": mapf_reset has not been called")
+    if (!e->has_scenario) return fail(MAPF_E_STATE, name ": mapf_reset has not been called"); \
+    ON_DEVICE(e->cfg.device)
+#define WC(e, k) ((e)->d_work + 2 * (k))
 
 // vec is written with one 16-byte store per agent
 static int check_vec(const float *vec, const char *name) {
@@ -195,7 +247,7 @@ static int check_step_n(const MapfEnv *e, const char *name) {
 }
 // N <= 32: lane = agent (step.cu); 32 < N <= 128: lane loops over agents (step_wide.cu)
 static cudaError_t do_step(MapfEnv *e, const int8_t *actions, const int8_t *status, const MapfStepOut &o, int mode, cudaStream_t s) {
-    if (e->v.N <= 32) return launch_step(e->v, actions, status, o, mode, e->d_work, s);
+    if (e->v.N <= 32) return launch_step(e->v, actions, status, o, mode, WC(e, WC_STEP), s);
     return launch_step_wide(e->v, actions, status, o, mode, s);
 }
 
@@ -231,7 +283,7 @@ int mapf_observe(MapfEnv *e, float *obs, float *vec, void *stream) {
     NEED_ENV("mapf_observe");
     if (int rc = check_vec(vec, "mapf_observe")) return rc;
     if (!obs || !vec) return fail(MAPF_E_NULL, "mapf_observe: null argument");
-    CU(launch_observe(e->v, obs, vec, e->d_work, (cudaStream_t)stream));
+    CU(launch_observe(e->v, obs, vec, WC(e, WC_OBSERVE), (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -242,10 +294,10 @@ int mapf_step_observe(MapfEnv *e, const int8_t *actions, const MapfStepOut *out,
     if (int rc = check_step_n(e, "mapf_step_observe")) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (step_observe_fusable(e->v) && !(e->v.dbg_flags & 1)) {
-        CU(launch_step_observe(e->v, actions, *out, obs, vec, e->d_work, s));
+        CU(launch_step_observe(e->v, actions, *out, obs, vec, WC(e, WC_FUSED), s));
     } else {
         CU(do_step(e, actions, nullptr, *out, MODE_FUSED, s));
-        CU(launch_observe(e->v, obs, vec, e->d_work, s));
+        CU(launch_observe(e->v, obs, vec, WC(e, WC_OBSERVE), s));
     }
     return MAPF_OK;
 }
@@ -255,7 +307,7 @@ int mapf_observe_bf16(MapfEnv *e, uint16_t *obs_bf16, float *vec, void *stream) 
     NEED_ENV("mapf_observe_bf16");
     if (int rc = check_vec(vec, "mapf_observe_bf16")) return rc;
     if (!obs_bf16 || !vec) return fail(MAPF_E_NULL, "mapf_observe_bf16: null argument");
-    CU(launch_observe(e->v, reinterpret_cast<float *>(obs_bf16), vec, e->d_work, (cudaStream_t)stream, 1));
+    CU(launch_observe(e->v, reinterpret_cast<float *>(obs_bf16), vec, WC(e, WC_OBSERVE), (cudaStream_t)stream, 1));
     return MAPF_OK;
 }
 
@@ -267,10 +319,10 @@ int mapf_step_observe_bf16(MapfEnv *e, const int8_t *actions, const MapfStepOut 
     cudaStream_t s = (cudaStream_t)stream;
     float *obs = reinterpret_cast<float *>(obs_bf16);
     if (step_observe_fusable(e->v) && !(e->v.dbg_flags & 1)) {
-        CU(launch_step_observe(e->v, actions, *out, obs, vec, e->d_work, s, 1));
+        CU(launch_step_observe(e->v, actions, *out, obs, vec, WC(e, WC_FUSED), s, 1));
     } else {
         CU(do_step(e, actions, nullptr, *out, MODE_FUSED, s));
-        CU(launch_observe(e->v, obs, vec, e->d_work, s, 1));
+        CU(launch_observe(e->v, obs, vec, WC(e, WC_OBSERVE), s, 1));
     }
     return MAPF_OK;
 }
@@ -281,7 +333,7 @@ int mapf_bfs(MapfEnv *e, const int32_t *agent_list, int64_t n, int16_t *out, voi
     if (!agent_list) n = (int64_t)e->v.W * e->v.N;
     if (n < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_bfs: n < 0");
     if (n == 0) return MAPF_OK;
-    CU(launch_bfs(e->v, agent_list, n, nullptr, out, 0, e->d_work_bfs, (cudaStream_t)stream));
+    CU(launch_bfs(e->v, agent_list, n, nullptr, out, 0, WC(e, WC_BFS), (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -289,7 +341,7 @@ int mapf_bfs_refresh(MapfEnv *e, const uint8_t *goals_reached, int16_t *bfs_maps
     NEED_ENV("mapf_bfs_refresh");
     if (!goals_reached || !bfs_maps) return fail(MAPF_E_NULL, "mapf_bfs_refresh: null argument");
     CU(launch_arrivals(e->v, goals_reached, e->d_list, e->d_count, (cudaStream_t)stream));
-    CU(launch_bfs(e->v, e->d_list, (long long)e->v.W * e->v.N, e->d_count, bfs_maps, 1, e->d_work_bfs, (cudaStream_t)stream));
+    CU(launch_bfs(e->v, e->d_list, (long long)e->v.W * e->v.N, e->d_count, bfs_maps, 1, WC(e, WC_BFS), (cudaStream_t)stream));
     return MAPF_OK;
 }
 
@@ -330,19 +382,28 @@ int mapf_generate_scenario(const MapfGenConfig *c, uint8_t *obst, int16_t *dims,
         if (c->size_lo > 0 && (c->size_hi < c->size_lo || c->size_hi > c->height || c->size_hi > c->width))
             return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: size range does not fit height x width");
     } else return fail(MAPF_E_BAD_CONFIG, "mapf_generate_scenario: kind must be 0 (density) or 1 (warehouse)");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CU(launch_scenario_gen(*c, obst, dims, starts, goal_queue, htrace, hlen, hp5, gen_err, (cudaStream_t)stream));
     return MAPF_OK;
 }
 
 int mapf_get_state(MapfEnv *e, int16_t *pos, int16_t *goal, int8_t *rep, uint32_t *err, void *stream) {
     if (!e) return fail(MAPF_E_NULL, "mapf_get_state: null env");
+    ON_DEVICE(e->cfg.device);
     const size_t WN = (size_t)e->v.W * e->v.N;
     cudaStream_t s = (cudaStream_t)stream;
     if (pos) CU(cudaMemcpyAsync(pos, e->v.pos, WN * 4, cudaMemcpyDeviceToDevice, s));
     if (goal) CU(cudaMemcpyAsync(goal, e->v.goal, WN * 4, cudaMemcpyDeviceToDevice, s));
     if (rep) CU(cudaMemcpyAsync(rep, e->v.rep, WN, cudaMemcpyDeviceToDevice, s));
     if (err) CU(cudaMemcpyAsync(err, e->v.err, (size_t)e->v.W * 4, cudaMemcpyDeviceToDevice, s));
+    return MAPF_OK;
+}
+
+int mapf_get_human(MapfEnv *e, int16_t *pos_next, int32_t *tick, void *stream) {
+    NEED_ENV("mapf_get_human");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pos_next) CU(cudaMemcpyAsync(pos_next, e->v.hcur, (size_t)e->v.W * 8, cudaMemcpyDeviceToDevice, s));
+    if (tick) CU(cudaMemcpyAsync(tick, e->v.htick, (size_t)e->v.W * 4, cudaMemcpyDeviceToDevice, s));
     return MAPF_OK;
 }
 
@@ -398,7 +459,96 @@ int mapf_load_state(MapfEnv *e, const void *blob, void *stream) {
 
 int mapf_get_counters(MapfEnv *e, int64_t *counters, void *stream) {
     if (!e || !counters) return fail(MAPF_E_NULL, "mapf_get_counters: null argument");
+    ON_DEVICE(e->cfg.device);
     CU(cudaMemcpyAsync(counters, e->v.counters, (size_t)e->v.W * 6 * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------------------------
+namespace {
+
+MapfStepOut slot_ptrs(const MapfEnv *e, int k) {
+    unsigned char *b = e->d_slot[k];
+    const MapfHostLayout &L = e->lay;
+    MapfStepOut o;
+    memset(&o, 0, sizeof(o));
+    o.reward = reinterpret_cast<float *>(b + L.off_reward);
+    o.cost = reinterpret_cast<float *>(b + L.off_cost);
+    o.shadow_goals = reinterpret_cast<int32_t *>(b + L.off_shadow_goals);
+    o.status = reinterpret_cast<int8_t *>(b + L.off_status);
+    o.goals_reached = b + L.off_goals_reached;
+    o.violated = b + L.off_violated;
+    o.fixed_actions = reinterpret_cast<int8_t *>(b + L.off_fixed_actions);
+    return o;
+}
+
+// Queue the joint action's host-to-device copy for slot k on the env's h2d stream and make `s` wait for it.  The buffer
+// d_actions[k] was last read by the kernels of the begin two calls ago (ev_step[k]); the copy may therefore overlap the
+// kernels of the previous begin.
+int queue_actions(MapfEnv *e, int k, const int8_t *actions_host, cudaStream_t s) {
+    const size_t WN = (size_t)e->v.W * e->v.N;
+    if (e->begun >= 2) CU(cudaStreamWaitEvent(e->h2d_stream, e->ev_step[k], 0));
+    else CU(cudaStreamWaitEvent(e->h2d_stream, e->ev_step[k ^ 1], 0));     // (first calls: order behind whatever ran last)
+    CU(cudaMemcpyAsync(e->d_actions[k], actions_host, WN, cudaMemcpyHostToDevice, e->h2d_stream));
+    CU(cudaEventRecord(e->ev_h2d[k], e->h2d_stream));
+    CU(cudaStreamWaitEvent(s, e->ev_h2d[k], 0));
+    // the device slot k is overwritten by this step: its previous contents must have left for the host
+    if (e->begun >= 2) CU(cudaStreamWaitEvent(s, e->ev_copied[k], 0));
+    // a trainValid copy of the previous begin reads the caller's tensor that this step may overwrite
+    if (e->begun >= 1 && e->tv_copy_pending[k ^ 1]) CU(cudaStreamWaitEvent(s, e->ev_copied[k ^ 1], 0));
+    return MAPF_OK;
+}
+
+}  // namespace
+
+int mapf_host_layout(MapfEnv *e, int with_train_valid, MapfHostLayout *out) {
+    if (!e || !out) return fail(MAPF_E_NULL, "mapf_host_layout: null argument");
+    *out = e->lay;
+    if (with_train_valid) {
+        out->off_train_valid = out->slot_bytes;
+        out->slot_bytes += (int64_t)((((size_t)e->v.W * e->v.N * NA * 4) + 255) & ~(size_t)255);
+    }
+    return MAPF_OK;
+}
+
+int mapf_step_observe_host_begin(MapfEnv *e, const int8_t *actions_host, void *result_slot_host, int with_train_valid,
+                                 float *obs_dev, float *vec_dev, float *train_valid_dev, void *stream) {
+    NEED_ENV("mapf_step_observe_host_begin");
+    if (int rc = check_vec(vec_dev, "mapf_step_observe_host_begin")) return rc;
+    if (!actions_host || !result_slot_host || !obs_dev || !vec_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host_begin: null argument");
+    if (with_train_valid && !train_valid_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host_begin: with_train_valid needs train_valid_dev");
+    if (int rc = check_step_n(e, "mapf_step_observe_host_begin")) return rc;
+    const EnvView &v = e->v;
+    cudaStream_t s = (cudaStream_t)stream, cs = e->copy_stream;
+    const int k = e->next_slot;
+    if (int rc = queue_actions(e, k, actions_host, s)) return rc;
+    MapfStepOut o = slot_ptrs(e, k);
+    o.train_valid = train_valid_dev;
+    if (step_observe_fusable(v) && !(v.dbg_flags & 1)) {
+        CU(launch_step_observe(v, e->d_actions[k], o, obs_dev, vec_dev, WC(e, WC_FUSED), s));
+    } else {
+        CU(do_step(e, e->d_actions[k], nullptr, o, MODE_FUSED, s));
+        CU(launch_observe(v, obs_dev, vec_dev, WC(e, WC_OBSERVE), s));
+    }
+    CU(cudaEventRecord(e->ev_step[k], s));
+    CU(cudaStreamWaitEvent(cs, e->ev_step[k], 0));
+    CU(cudaMemcpyAsync(result_slot_host, e->d_slot[k], (size_t)e->lay.slot_bytes, cudaMemcpyDeviceToHost, cs));   // ONE copy
+    if (with_train_valid)
+        CU(cudaMemcpyAsync(static_cast<char *>(result_slot_host) + e->lay.slot_bytes, train_valid_dev,
+                           (size_t)v.W * v.N * NA * 4, cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(e->ev_copied[k], cs));
+    e->tv_copy_pending[k] = with_train_valid != 0;
+    e->next_slot = k ^ 1;
+    if (e->begun < 2) e->begun++;
+    return MAPF_OK;
+}
+
+int mapf_step_observe_host_wait(MapfEnv *e, int age) {
+    if (!e) return fail(MAPF_E_NULL, "mapf_step_observe_host_wait: null env");
+    if (age < 0 || age > 1) return fail(MAPF_E_BAD_CONFIG, "mapf_step_observe_host_wait: age must be 0 or 1");
+    if (e->begun <= age) return fail(MAPF_E_STATE, "mapf_step_observe_host_wait: no such begin in flight");
+    const int k = (e->next_slot ^ 1) ^ age;
+    CU(cudaEventSynchronize(e->ev_copied[k]));
     return MAPF_OK;
 }
 
@@ -407,56 +557,31 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
     NEED_ENV("mapf_step_observe_host");
     if (int rc = check_vec(vec_dev, "mapf_step_observe_host")) return rc;
     if (!actions_host || !out || !obs_dev || !vec_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host: null argument");
+    if (out->train_valid && !train_valid_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host: out->train_valid needs train_valid_dev");
     if (int rc = check_step_n(e, "mapf_step_observe_host")) return rc;
     const EnvView &v = e->v;
     const size_t W = v.W, WN = (size_t)v.W * v.N;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (!e->staging) {
-        CU(cudaMalloc((void **)&e->d_actions, WN));
-        CU(cudaMalloc((void **)&e->d_out.status, WN));
-        CU(cudaMalloc((void **)&e->d_out.reward, WN * 4));
-        CU(cudaMalloc((void **)&e->d_out.cost, WN * 4));
-        CU(cudaMalloc((void **)&e->d_out.train_valid, WN * NA * 4));
-        CU(cudaMalloc((void **)&e->d_out.goals_reached, WN));
-        CU(cudaMalloc((void **)&e->d_out.violated, WN));
-        CU(cudaMalloc((void **)&e->d_out.shadow_goals, W * 4));
-        CU(cudaMalloc((void **)&e->d_out.fixed_actions, WN));
-        CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
-        e->staging = true;
-    }
-    // MAPF_DBG_FLAGS bit 20: print the device timeline of this call (timing events; experiments only)
-    const bool tl = (v.dbg_flags >> 20) & 1;
-    static cudaEvent_t t_ev[6];
-    static bool t_init = false;
-    if (tl && !t_init) { for (auto &x : t_ev) cudaEventCreate(&x); t_init = true; }
-    if (tl) cudaEventRecord(t_ev[0], s);
-    CU(cudaMemcpyAsync(e->d_actions, actions_host, WN, cudaMemcpyHostToDevice, s));
-    if (tl) cudaEventRecord(t_ev[1], s);
-    MapfStepOut o = e->d_out;                                   // only compute what the caller asked for
+    cudaStream_t s = (cudaStream_t)stream, cs = e->copy_stream;
+    const int k = e->next_slot;
+    if (int rc = queue_actions(e, k, actions_host, s)) return rc;
+    MapfStepOut o = slot_ptrs(e, k);                            // only compute what the caller asked for
     if (!out->status) o.status = nullptr;
     if (!out->reward) o.reward = nullptr;
     if (!out->cost) o.cost = nullptr;
-    if (train_valid_dev) o.train_valid = train_valid_dev;
-    else if (!out->train_valid) o.train_valid = nullptr;
+    o.train_valid = train_valid_dev;
     if (!out->goals_reached) o.goals_reached = nullptr;
     if (!out->violated) o.violated = nullptr;
     if (!out->shadow_goals) o.shadow_goals = nullptr;
     if (!out->fixed_actions) o.fixed_actions = nullptr;
-    CU(do_step(e, e->d_actions, nullptr, o, MODE_FUSED, s));
-    // The per-agent step results are final once step_kernel has run: copy them to the host on a second stream while
-    // observe_kernel writes the observations (the copy engine and the SMs overlap; ~25 MB over PCIe vs ~0.7 ms of stores).
-    // Measured alternatives at 65 536 x 32 agents: this split 0.97 ms per call; the fused kernel followed by the copies
-    // 1.33 ms (the copy is exposed); the fused kernel pipelined over four world ranges 1.18 ms (short launches lose the
-    // prefetch and tail efficiency).  Hence the two-kernel form here, the fused launch for device-resident callers.
-    cudaStream_t cs = e->copy_stream;
-    CU(cudaEventRecord(e->ev_step, s));
-    if (tl) cudaEventRecord(t_ev[2], s);
-    CU(cudaStreamWaitEvent(cs, e->ev_step, 0));
-    if (tl) cudaEventRecord(t_ev[4], cs);
-    CU(launch_observe(v, obs_dev, vec_dev, e->d_work, s));
-    if (tl) cudaEventRecord(t_ev[3], s);
+    // Synchronous form: the caller blocks until the results are on the host, so the copy has to hide inside this call.
+    // The per-agent results are final once step_kernel has run: they travel on the copy stream while observe_kernel
+    // writes the observations (measured at 65 536 x 32 agents: this split 0.97 ms per call; the fused kernel followed by
+    // the copies 1.33 ms, the copy being exposed).  The split-phase form above uses the fused launch instead and hides the
+    // copy behind the NEXT step.
+    CU(do_step(e, e->d_actions[k], nullptr, o, MODE_FUSED, s));
+    CU(cudaEventRecord(e->ev_step[k], s));
+    CU(cudaStreamWaitEvent(cs, e->ev_step[k], 0));
+    CU(launch_observe(v, obs_dev, vec_dev, WC(e, WC_OBSERVE), s));
     if (out->status) CU(cudaMemcpyAsync(out->status, o.status, WN, cudaMemcpyDeviceToHost, cs));
     if (out->reward) CU(cudaMemcpyAsync(out->reward, o.reward, WN * 4, cudaMemcpyDeviceToHost, cs));
     if (out->cost) CU(cudaMemcpyAsync(out->cost, o.cost, WN * 4, cudaMemcpyDeviceToHost, cs));
@@ -465,20 +590,24 @@ int mapf_step_observe_host(MapfEnv *e, const int8_t *actions_host, const MapfSte
     if (out->violated) CU(cudaMemcpyAsync(out->violated, o.violated, WN, cudaMemcpyDeviceToHost, cs));
     if (out->shadow_goals) CU(cudaMemcpyAsync(out->shadow_goals, o.shadow_goals, W * 4, cudaMemcpyDeviceToHost, cs));
     if (out->fixed_actions) CU(cudaMemcpyAsync(out->fixed_actions, o.fixed_actions, WN, cudaMemcpyDeviceToHost, cs));
-    CU(cudaEventRecord(e->ev_copied, cs));
-    if (tl) cudaEventRecord(t_ev[5], cs);
+    CU(cudaEventRecord(e->ev_copied[k], cs));
+    e->tv_copy_pending[k] = false;
+    e->next_slot = k ^ 1;
+    if (e->begun < 2) e->begun++;
     const size_t PB = (size_t)v.C * v.F * v.F;
     if (obs_host) CU(cudaMemcpyAsync(obs_host, obs_dev, WN * PB * 4, cudaMemcpyDeviceToHost, s));
     if (vec_host) CU(cudaMemcpyAsync(vec_host, vec_dev, WN * 16, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamWaitEvent(s, e->ev_copied, 0));
+    CU(cudaStreamWaitEvent(s, e->ev_copied[k], 0));
     CU(cudaStreamSynchronize(s));
-    if (tl) {
-        float a = 0, b = 0, c = 0, d = 0, f = 0;
-        cudaEventElapsedTime(&a, t_ev[0], t_ev[1]); cudaEventElapsedTime(&b, t_ev[1], t_ev[2]);
-        cudaEventElapsedTime(&c, t_ev[2], t_ev[3]); cudaEventElapsedTime(&d, t_ev[4], t_ev[5]);
-        cudaEventElapsedTime(&f, t_ev[0], t_ev[5]);
-        fprintf(stderr, "[mapf timeline] h2d %.3f ms, step %.3f, observe %.3f, d2h copies %.3f (done %.3f after start)\n", a, b, c, d, f);
-    }
+    return MAPF_OK;
+}
+
+int mapf_checksum_rows(const void *data, int64_t rows, int64_t row_bytes, uint64_t *out, void *stream) {
+    if (!data || !out) return fail(MAPF_E_NULL, "mapf_checksum_rows: null argument");
+    if (rows < 0 || row_bytes < 0 || (row_bytes & 3) || (reinterpret_cast<uintptr_t>(data) & 3))
+        return fail(MAPF_E_BAD_CONFIG, "mapf_checksum_rows: rows >= 0, row_bytes a multiple of 4, data 4-byte aligned");
+    if (rows == 0) return MAPF_OK;
+    CU(launch_checksum_rows(static_cast<const uint32_t *>(data), rows, row_bytes / 4, reinterpret_cast<unsigned long long *>(out), (cudaStream_t)stream));
     return MAPF_OK;
 }
 

@@ -24,13 +24,14 @@ struct WideSmem {
     uint32_t *pos;       // [N] packed cell
     uint32_t *goal;      // [N]
     uint32_t *mm;        // [N] conflict partners of the chosen action, one id per byte
+    uint32_t *npos;      // [N] packed cell after the move
     uint8_t *inv0, *inv1, *restr, *good, *confl;   // [N] 5-bit masks
     int8_t *act, *rep, *cls, *st, *commit;         // [N]
     uint8_t *queue;      // [256] ring of agent ids
 };
 
 __host__ __device__ inline size_t wide_bytes(int HP, int RW, int GS) {
-    return al16((size_t)HP * RW * 4) + al16((size_t)HP * GS) + NMAX * 5 * 4 + NMAX * 4 * 3 + NMAX * 10 + 256;
+    return al16((size_t)HP * RW * 4) + al16((size_t)HP * GS) + NMAX * 5 * 4 + NMAX * 4 * 4 + NMAX * 10 + 256;
 }
 
 __device__ inline WideSmem wide_carve(unsigned char *b, int HP, int RW, int GS) {
@@ -41,6 +42,7 @@ __device__ inline WideSmem wide_carve(unsigned char *b, int HP, int RW, int GS) 
     s.pos = reinterpret_cast<uint32_t *>(b); b += NMAX * 4;
     s.goal = reinterpret_cast<uint32_t *>(b); b += NMAX * 4;
     s.mm = reinterpret_cast<uint32_t *>(b); b += NMAX * 4;
+    s.npos = reinterpret_cast<uint32_t *>(b); b += NMAX * 4;
     s.inv0 = b; b += NMAX; s.inv1 = b; b += NMAX; s.restr = b; b += NMAX; s.good = b; b += NMAX; s.confl = b; b += NMAX;
     s.act = reinterpret_cast<int8_t *>(b); b += NMAX; s.rep = reinterpret_cast<int8_t *>(b); b += NMAX;
     s.cls = reinterpret_cast<int8_t *>(b); b += NMAX; s.st = reinterpret_cast<int8_t *>(b); b += NMAX;
@@ -164,6 +166,7 @@ step_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8
                 out.cost[base + i] = d2 < 25 ? (float)((5.0 - sqrt((double)d2)) / 5.0) : 0.0f;
             }
             if (MODE == MODE_EVALUATE && out.reward) out.reward[base + i] = st == ST_REPEAT ? -0.35f : st == ST_OK ? -0.3f : -2.0f;
+            if (MODE == MODE_EVALUATE && out.good_actions) out.good_actions[base + i] = s.good[i];
             if (out.train_valid) {
                 const uint32_t good = s.good[i], restr = s.restr[i], confl = s.confl[i];
 #pragma unroll
@@ -273,9 +276,12 @@ step_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8
         const int nr_ = (int16_t)(pw & 0xffff) + dr_of(f), nc_ = (int16_t)(pw >> 16) + dc_of(f);
         const bool arrived = nr_ == (int16_t)(gw & 0xffff) && nc_ == (int16_t)(gw >> 16);
         const bool viol = (h2r - nr_) * (h2r - nr_) + (h2c - nc_) * (h2c - nc_) <= 24;
-        reinterpret_cast<uint32_t *>(v.pos)[base + i] = (uint32_t)(uint16_t)nr_ | ((uint32_t)(uint16_t)nc_ << 16);
+        const uint32_t npw = (uint32_t)(uint16_t)nr_ | ((uint32_t)(uint16_t)nc_ << 16);
+        reinterpret_cast<uint32_t *>(v.pos)[base + i] = npw;
+        s.npos[i] = npw;
+        s.cls[i] = (int8_t)arrived;                 // (the class array is free again: arrival flags for goal sampling)
         v.rep[base + i] = (int8_t)opp_of(f);
-        if (arrived) {
+        if (arrived && !v.goal_sampling) {
             int k = v.qcur[base + i];
             if (k >= v.Q) k = v.Q - 1; else v.qcur[base + i] = k + 1;
             reinterpret_cast<uint32_t *>(v.goal)[base + i] = reinterpret_cast<const uint32_t *>(v.goal_queue)[(base + i) * v.Q + k];
@@ -291,6 +297,35 @@ step_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8
         n_arr += arrived; n_viol += viol;
     }
     n_arr = __reduce_add_sync(FULL, n_arr); n_viol = __reduce_add_sync(FULL, n_viol);
+    if (v.goal_sampling && n_arr) {
+        // MapfGym.getNextGoal on arrival (mapf_gym.py:626, util.py:67-76); same draws as resolve_world (step_world.cuh)
+        __syncwarp();
+        int rows = v.H, cols = v.Wd;
+        if (v.dims) { rows = v.dims[2 * w]; cols = v.dims[2 * w + 1]; }
+        const uint32_t nstep_w = (uint32_t)v.nstep[w];
+        uint32_t draw = 0;
+        for (int i = 0; i < N; ++i) {
+            if (!s.cls[i]) continue;                                 // warp-uniform (shared memory)
+            uint32_t chosen = 0;
+            bool found = false;
+            for (int batch = 0; batch < GOAL_DRAW_CAP / 32 && !found; ++batch) {
+                const uint32_t cand = goal_candidate(v.seed, (uint32_t)(w + v.world_offset), nstep_w, draw + lane, rows, cols);
+                const int cr = (int)(cand & 0xffff), cc = (int)(cand >> 16);
+                bool free_ = !row_bit(s.obits + (cr + P) * RW, cc + P);
+                for (int j = 0; j < N && free_; ++j)
+                    free_ = cand != (j <= i ? s.npos[j] : s.pos[j]) && cand != s.goal[j];
+                const uint32_t b = __ballot_sync(FULL, free_);
+                if (b) { const int k = __ffs(b) - 1; chosen = __shfl_sync(FULL, cand, k); draw += k + 1; found = true; }
+                else draw += 32;
+            }
+            if (!found) errbits |= MAPF_ERR_NO_FREE_CELL;
+            else {
+                __syncwarp();
+                if (lane == 0) { s.goal[i] = chosen; reinterpret_cast<uint32_t *>(v.goal)[base + i] = chosen; }
+                __syncwarp();
+            }
+        }
+    }
     n_c1 = __reduce_add_sync(FULL, n_c1); n_c2 = __reduce_add_sync(FULL, n_c2); n_c3 = __reduce_add_sync(FULL, n_c3);
     const uint32_t eb = __reduce_or_sync(FULL, errbits);
     if (lane == 0) {

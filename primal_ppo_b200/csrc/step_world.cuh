@@ -183,6 +183,7 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
                 out.cost[idx] = d2 < 25 ? (float)((5.0 - sqrt((double)d2)) / 5.0) : 0.0f;
             }
             if (MODE == MODE_EVALUATE && out.reward) out.reward[idx] = reward;
+            if (MODE == MODE_EVALUATE && out.good_actions) out.good_actions[idx] = (uint8_t)good;   // allGoodActions (:404-430)
         }
         if (lane == 0 && out.shadow_goals) out.shadow_goals[w] = __popc(sgm);
         if (out.train_valid) {
@@ -330,13 +331,48 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
     const bool viol = active && ((h2r - nr_) * (h2r - nr_) + (h2c - nc_) * (h2c - nc_) <= 24);   // cost_norm >= 0.01
     new_pw = (uint32_t)(uint16_t)nr_ | ((uint32_t)(uint16_t)nc_ << 16);
     new_gw = gw;
+    const uint32_t am = __ballot_sync(FULL, arrived);
+    if (v.goal_sampling && am) {
+        // MapfGym.getNextGoal (mapf_gym.py:189-190, 626) = getFreeCell(worldWithAgentsAndGoals()) (util.py:67-76), for the
+        // arrived agents in agent order: a cell is taken if it is an obstacle, the cell of an agent (agents <= i have
+        // moved, the others have not: jointStep's loop is sequential, :620-627) or any agent's current goal.  The warp tests
+        // 32 consecutive draws at a time and takes the first free one, which is what the sequential rejection loop does.
+        int rows = v.H, cols = v.Wd;
+        if (v.dims) { rows = v.dims[2 * w]; cols = v.dims[2 * w + 1]; }
+        const uint32_t nstep_w = (uint32_t)v.nstep[w];
+        uint32_t m = am, draw = 0;
+        while (m) {
+            const int i = __ffs(m) - 1; m &= m - 1;
+            const uint32_t occ = (lane <= i) ? new_pw : pw;
+            uint32_t chosen = 0;
+            bool found = false;
+            for (int batch = 0; batch < GOAL_DRAW_CAP / 32 && !found; ++batch) {
+                const uint32_t cand = goal_candidate(v.seed, (uint32_t)(w + v.world_offset), nstep_w, draw + lane, rows, cols);
+                const int cr = (int)(cand & 0xffff), cc = (int)(cand >> 16);
+                bool free_;
+                if (PACKED_OB) { const int ci = cr * v.Wd + cc; free_ = !((s.obits[ci >> 5] >> (ci & 31)) & 1u); }
+                else free_ = !row_bit(s.obits + (cr + P) * RW, cc + P);
+                for (int j = 0; j < N; ++j) {
+                    const uint32_t pj = __shfl_sync(FULL, occ, j), gj = __shfl_sync(FULL, new_gw, j);
+                    free_ = free_ && cand != pj && cand != gj;
+                }
+                const uint32_t b = __ballot_sync(FULL, free_);
+                if (b) { const int k = __ffs(b) - 1; chosen = __shfl_sync(FULL, cand, k); draw += k + 1; found = true; }
+                else draw += 32;
+            }
+            if (!found) errbits |= MAPF_ERR_NO_FREE_CELL;          // goal unchanged (= the agent's own cell)
+            else if (lane == i) new_gw = chosen;
+        }
+    }
     if (active) {
         st_keep(reinterpret_cast<uint32_t *>(v.pos) + idx, new_pw, pol);
         st_keep_s8(v.rep + idx, opp_of(f), pol);                                 // takeStep :158-161
-        if (arrived) {                                                           // Sequence.getNext util.py:33-39
-            int k = v.qcur[idx];
-            if (k >= v.Q) k = v.Q - 1; else v.qcur[idx] = k + 1;
-            new_gw = reinterpret_cast<const uint32_t *>(v.goal_queue)[idx * v.Q + k];
+        if (arrived) {
+            if (!v.goal_sampling) {                                              // Sequence.getNext util.py:33-39
+                int k = v.qcur[idx];
+                if (k >= v.Q) k = v.Q - 1; else v.qcur[idx] = k + 1;
+                new_gw = reinterpret_cast<const uint32_t *>(v.goal_queue)[idx * v.Q + k];
+            }
             st_keep(reinterpret_cast<uint32_t *>(v.goal) + idx, new_gw, pol);
         }
         if (out.goals_reached) out.goals_reached[idx] = arrived;
@@ -344,7 +380,7 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
         if (out.fixed_actions) out.fixed_actions[idx] = (int8_t)f;
         if (MODE == MODE_FUSED && out.reward) out.reward[idx] = arrived ? __fadd_rn(reward, 1.5f) : reward;  // runner.py:89-91
     }
-    const uint32_t am = __ballot_sync(FULL, arrived), vm_ = __ballot_sync(FULL, viol);
+    const uint32_t vm_ = __ballot_sync(FULL, viol);
     const uint32_t c1 = __ballot_sync(FULL, active && st == ST_STATIC), c2b = __ballot_sync(FULL, active && st == ST_HUMAN),
                    c3 = __ballot_sync(FULL, active && st == ST_AGENT);
     const uint32_t eb = __reduce_or_sync(FULL, errbits);

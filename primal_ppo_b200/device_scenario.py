@@ -40,13 +40,19 @@ class DeviceScenario:
     num_agents = property(lambda s: int(s.starts.shape[1]))
 
     def validate(self) -> None:
+        """Shape / dtype checks (ValueError).  The arrays come from `mapf_generate_scenario`, which only ever emits cells
+        inside the world and on free cells; their values are therefore not re-checked here (that would be a host sync)."""
+        def need(cond, msg):
+            if not cond:
+                raise ValueError("DeviceScenario: " + msg)
         W, N = self.num_worlds, self.num_agents
-        assert self.obst.dtype == torch.uint8 and self.obst.is_cuda and self.obst.is_contiguous()
-        assert self.starts.shape == (W, N, 2) and self.starts.dtype == torch.int16
-        assert self.goal_queue.shape[:2] == (W, N) and self.goal_queue.shape[3] == 2 and self.goal_queue.dtype == torch.int16
-        assert self.htrace.shape[0] == W and self.htrace.shape[2] == 4 and self.htrace.dtype == torch.int16
-        assert self.hlen.shape == (W,) and self.hlen.dtype == torch.int32
-        assert self.fov % 2 == 1 and self.fov >= 3 and self.num_channel in (5, 6)
+        need(self.obst.dtype == torch.uint8 and self.obst.is_cuda and self.obst.is_contiguous(), "obst must be a contiguous CUDA uint8 tensor")
+        need(self.starts.shape == (W, N, 2) and self.starts.dtype == torch.int16, "starts must be int16 [W,N,2]")
+        need(self.goal_queue.shape[:2] == (W, N) and self.goal_queue.shape[3] == 2 and self.goal_queue.dtype == torch.int16,
+             "goal_queue must be int16 [W,N,Q,2]")
+        need(self.htrace.shape[0] == W and self.htrace.shape[2] == 4 and self.htrace.dtype == torch.int16, "htrace must be int16 [W,L,4]")
+        need(self.hlen.shape == (W,) and self.hlen.dtype == torch.int32, "hlen must be int32 [W]")
+        need(self.fov % 2 == 1 and self.fov >= 3 and self.num_channel in (5, 6), "fov odd >= 3, num_channel 5 or 6")
 
     def to_host(self) -> Scenario:
         n = lambda t: None if t is None else t.cpu().numpy()

@@ -67,31 +67,50 @@ class Scenario:
         return int(self.starts.shape[1])
 
     def validate(self) -> None:
+        """Shape / dtype / range checks; raises ValueError (the kernels index shared memory with these values, so an
+        out-of-range cell would be a silent out-of-bounds access, not an err[w] flag)."""
+        def need(cond, msg):
+            if not cond:
+                raise ValueError("Scenario: " + msg)
+        need(self.obst.ndim == 3 and self.obst.dtype == np.uint8, "obst must be uint8 [W,H,Wd]")
         W, H, Wd = self.obst.shape
         N = self.num_agents
-        assert self.obst.dtype == np.uint8
-        assert self.starts.shape == (W, N, 2) and self.starts.dtype == np.int16
-        assert self.goal_queue.ndim == 4 and self.goal_queue.shape[:2] == (W, N)
-        assert self.goal_queue.shape[3] == 2 and self.goal_queue.dtype == np.int16
-        assert self.goal_queue.shape[2] >= 1
-        assert self.htrace.ndim == 3 and self.htrace.shape[0] == W and self.htrace.shape[2] == 4
-        assert self.htrace.dtype == np.int16
-        assert self.hlen.shape == (W,) and self.hlen.dtype == np.int32
-        assert np.all(self.hlen >= 1) and np.all(self.hlen <= self.htrace.shape[1])
-        assert self.fov % 2 == 1 and self.fov >= 3
-        assert self.num_channel in (5, 6)
+        need(self.starts.shape == (W, N, 2) and self.starts.dtype == np.int16, "starts must be int16 [W,N,2]")
+        need(self.goal_queue.ndim == 4 and self.goal_queue.shape[:2] == (W, N) and self.goal_queue.shape[3] == 2
+             and self.goal_queue.dtype == np.int16 and self.goal_queue.shape[2] >= 1, "goal_queue must be int16 [W,N,Q>=1,2]")
+        need(self.htrace.ndim == 3 and self.htrace.shape[0] == W and self.htrace.shape[2] == 4
+             and self.htrace.dtype == np.int16, "htrace must be int16 [W,L,4]")
+        need(self.hlen.shape == (W,) and self.hlen.dtype == np.int32, "hlen must be int32 [W]")
+        need(bool(np.all(self.hlen >= 1) and np.all(self.hlen <= self.htrace.shape[1])), "1 <= hlen <= L")
+        need(self.fov % 2 == 1 and self.fov >= 3, "fov must be odd and >= 3")
+        need(self.num_channel in (5, 6), "num_channel must be 5 or 6")
         if self.hp5 is not None:
-            assert self.hp5.dtype == np.int16
-            assert self.hp5.shape == (W, 5, 2) or self.hp5.shape == (W, self.htrace.shape[1], 5, 2)
+            need(self.hp5.dtype == np.int16 and (self.hp5.shape == (W, 5, 2) or self.hp5.shape == (W, self.htrace.shape[1], 5, 2)),
+                 "hp5 must be int16 [W,5,2] or [W,L,5,2]")
         if self.tape is not None:
-            assert self.tape.dtype == np.int8 and self.tape.shape[0] == W
-            assert self.tape_len is not None and self.tape_len.shape == (W,)
+            need(self.tape.dtype == np.int8 and self.tape.shape[0] == W, "tape must be int8 [W,TL]")
+            need(self.tape_len is not None and self.tape_len.shape == (W,), "tape needs tape_len [W]")
+        rows = np.full((W,), H, dtype=np.int64)
+        cols = np.full((W,), Wd, dtype=np.int64)
         if self.dims is not None:
-            assert self.dims.shape == (W, 2) and self.dims.dtype == np.int16
-            assert np.all(self.dims[:, 0] <= H) and np.all(self.dims[:, 1] <= Wd) and np.all(self.dims >= 1)
+            need(self.dims.shape == (W, 2) and self.dims.dtype == np.int16, "dims must be int16 [W,2]")
+            need(bool(np.all(self.dims[:, 0] <= H) and np.all(self.dims[:, 1] <= Wd) and np.all(self.dims >= 1)), "1 <= dims <= (H, Wd)")
             rr = np.arange(H)[None, :, None] >= self.dims[:, 0][:, None, None]
             cc = np.arange(Wd)[None, None, :] >= self.dims[:, 1][:, None, None]
-            assert np.all(self.obst[rr | cc] == 1), "cells outside dims must be obstacles"
+            need(bool(np.all(self.obst[rr | cc] == 1)), "cells outside dims must be obstacles")
+            rows, cols = self.dims[:, 0].astype(np.int64), self.dims[:, 1].astype(np.int64)
+        # starts and goals: inside the world's dims and on free cells
+        widx = np.arange(W)[:, None]
+        st = self.starts.astype(np.int64)
+        need(bool(np.all(st >= 0) and np.all(st[..., 0] < rows[:, None]) and np.all(st[..., 1] < cols[:, None])),
+             "starts outside the world")
+        need(bool(np.all(self.obst[widx, st[..., 0], st[..., 1]] == 0)), "starts on obstacle cells")
+        gq = self.goal_queue.astype(np.int64)
+        need(bool(np.all(gq >= 0) and np.all(gq[..., 0] < rows[:, None, None]) and np.all(gq[..., 1] < cols[:, None, None])),
+             "goals outside the world")
+        need(bool(np.all(self.obst[widx[:, :, None], gq[..., 0], gq[..., 1]] == 0)), "goals on obstacle cells")
+        ht = self.htrace.astype(np.int64)
+        need(bool(np.all(ht >= -1) and np.all(ht[..., 0::2] < H) and np.all(ht[..., 1::2] < Wd)), "human trace outside the grid")
 
     def slice(self, lo: int, hi: int) -> "Scenario":
         """Worlds [lo, hi) — how ranks shard a job (no communication on the env path)."""

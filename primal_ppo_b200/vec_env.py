@@ -17,6 +17,15 @@ Reference call                                     | batched call
 ``g, cv = env.jointStep(a, st)``                   | same -> u8 [W,N], u8 [W,N]
 (the five calls + ``rewards[g==1] += GOAL_REWARD``)| ``env.step(a)`` -> ``StepOut`` (one fused launch)
 ``agent.bfsMap``                                   | ``env.bfs_maps()`` -> int16 [W,N,H,Wd]
+``env.allGoodActions``                             | same -> uint8 [W,N] 5-bit masks (bit a = action a is good)
+``env._render()``                                  | ``env._render(world=0)`` -> uint8 frame of one world
+
+ALIASING.  The reference returns a fresh array from every call.  Here ``getActionStatus`` / ``calculateActionReward`` /
+``calculateCostReward`` / ``getTrainValid`` / ``jointStep`` / ``step`` return ENV-OWNED tensors that the next call
+overwrites (no allocation on the step path).  A runner that keeps results across steps — ``runner.py:84,93-94`` appends
+``trainVal`` / ``rewards`` / ``costRewards`` to lists — must either pass its own storage (``step(a, out=StepOut(...))``
+with slices of a rollout buffer, as ``ppo/trainer.py`` does) or construct the env with ``fresh_outputs=True``, which makes
+every getter return a clone (the reference's semantics, one extra device copy per call).
 """
 from __future__ import annotations
 
@@ -41,6 +50,7 @@ class StepOut:
     violated: torch.Tensor       # uint8 [W,N]
     shadow_goals: torch.Tensor   # int32 [W]
     fixed_actions: torch.Tensor  # int8  [W,N]
+    good_actions: Optional[torch.Tensor] = None   # uint8 [W,N] allGoodActions masks (mapf_evaluate only)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -49,7 +59,10 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class BatchedMapfGym:
     def __init__(self, scenario, device=None, seed: int = 1234, use_tape: bool = True,
-                 world_offset: int = 0):
+                 world_offset: int = 0, goal_sampling: bool = False, fresh_outputs: bool = False):
+        """goal_sampling: draw the next goal on device at arrival like ``MapfGym.getNextGoal`` (mapf_gym.py:189-190, 626;
+        util.getFreeCell) instead of popping the scenario's goal queues (``FixedMapfGym``, :668-669).
+        fresh_outputs: getters return clones instead of env-owned tensors (see ALIASING above)."""
         if not torch.cuda.is_available():
             raise _cabi.MapfError("BatchedMapfGym needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._lib = _cabi.load_library()
@@ -71,7 +84,9 @@ class BatchedMapfGym:
                                queue_len=int(sc.goal_queue.shape[2]), trace_len=int(sc.htrace.shape[1]),
                                tape_stride=0 if tape is None else int(tape.shape[1]),
                                hp5_per_tick=int(sc.hp5 is not None and sc.hp5.ndim == 4), seed=seed,
-                               device=self.device.index or 0, world_offset=int(world_offset))
+                               device=self.device.index or 0, world_offset=int(world_offset),
+                               goal_sampling=int(bool(goal_sampling)), reserved0=0)
+        self.goal_sampling, self._fresh = bool(goal_sampling), bool(fresh_outputs)
         h = C.c_void_p()
         _cabi.check(self._lib.mapf_create(C.byref(cfg), C.byref(h)), "mapf_create")
         self._h = h
@@ -88,6 +103,9 @@ class BatchedMapfGym:
         self._vec = None
         self._eval_key = None
         self._bfs = None
+        self._good = None
+        self._zero_actions = None
+        self._host_layouts = {}
         self.reset()
 
     # ------------------------------------------------------------------------------------------------------
@@ -149,7 +167,11 @@ class BatchedMapfGym:
         return _cabi.MapfStepOut(status=o.status.data_ptr(), reward=o.reward.data_ptr(), cost=o.cost.data_ptr(),
                                  train_valid=o.train_valid.data_ptr(), goals_reached=o.goals_reached.data_ptr(),
                                  violated=o.violated.data_ptr(), shadow_goals=o.shadow_goals.data_ptr(),
-                                 fixed_actions=o.fixed_actions.data_ptr())
+                                 fixed_actions=o.fixed_actions.data_ptr(),
+                                 good_actions=None if o.good_actions is None else o.good_actions.data_ptr())
+
+    def _ret(self, t):
+        return t.clone() if self._fresh else t
 
     # ---- the reference's five step calls (runner.py:64-87) -----------------------------------------------------
     def _evaluate(self, actions):
@@ -164,17 +186,53 @@ class BatchedMapfGym:
 
     def getActionStatus(self, actions):
         self._eval_key = None
-        return self._evaluate(actions).status
+        return self._ret(self._evaluate(actions).status)
 
     def calculateActionReward(self, actions, actionStatus=None):
         o = self._evaluate(actions)
-        return o.reward, o.shadow_goals
+        return self._ret(o.reward), self._ret(o.shadow_goals)
 
     def calculateCostReward(self, actions):
-        return self._evaluate(actions).cost
+        return self._ret(self._evaluate(actions).cost)
 
     def getTrainValid(self, actions):
-        return self._evaluate(actions).train_valid
+        return self._ret(self._evaluate(actions).train_valid)
+
+    @property
+    def allGoodActions(self):
+        """``MapfGym.allGoodActions`` (mapf_gym.py:169, 635: ``getUnconditionallyGoodActions(returnIsNeeded=True)``) of the
+        CURRENT state: uint8 [W,N], bit a set iff action a is unconditionally good for that agent (the reference holds a
+        list of sorted action arrays per agent; ``good_actions_lists`` converts).  Recomputed on access (the masks are a
+        pure function of the state and are never stored)."""
+        if self._good is None:
+            self._good = torch.empty((self.W, self.N), dtype=torch.uint8, device=self.device)
+            self._zero_actions = torch.zeros((self.W, self.N), dtype=torch.int8, device=self.device)
+        so = _cabi.MapfStepOut(good_actions=self._good.data_ptr())
+        _cabi.check(self._lib.mapf_evaluate(self._h, _ptr(self._zero_actions), C.byref(so), self._stream()), "mapf_evaluate")
+        return self._ret(self._good)
+
+    def good_actions_lists(self, world: int = 0):
+        """The reference's representation for one world: a list of N sorted int arrays."""
+        m = self.allGoodActions[world].cpu().numpy()
+        return [np.flatnonzero([(int(x) >> a) & 1 for a in range(5)]) for x in m]
+
+    def _render(self, world: int = 0, scale: int = 12):
+        """``MapfGym._render`` (mapf_gym.py:639-646) for one world: an RGB uint8 frame (own renderer, ``episode_io.render_world``;
+        not pixel-compatible with the reference's cv2 drawing)."""
+        from .episode_io import render_world
+        st = self.state()
+        obst = self._sc["obst"][world].cpu().numpy()
+        pos, goal = st["pos"][world].cpu().numpy(), st["goal"][world].cpu().numpy()
+        human = self.human()[0][world].cpu().numpy()
+        return render_world(obst, pos, goal, (int(human[0]), int(human[1])), scale=scale)
+
+    def human(self):
+        """``(human.getPos(), human.getNextPos(), tick)`` of every world (mapf_gym.py:25-50): int16 [W,2], int16 [W,2],
+        int32 [W]."""
+        pn = torch.empty((self.W, 4), dtype=torch.int16, device=self.device)
+        tick = torch.empty((self.W,), dtype=torch.int32, device=self.device)
+        _cabi.check(self._lib.mapf_get_human(self._h, _ptr(pn), _ptr(tick), self._stream()), "mapf_get_human")
+        return pn[:, :2], pn[:, 2:], tick
 
     def jointStep(self, actions, actionStatus):
         a = self._actions(actions)
@@ -183,7 +241,7 @@ class BatchedMapfGym:
         _cabi.check(self._lib.mapf_joint_step(self._h, _ptr(a), _ptr(st), _ptr(o.goals_reached), _ptr(o.violated),
                                               _ptr(o.fixed_actions), self._stream()), "mapf_joint_step")
         self._eval_key = None
-        return o.goals_reached, o.violated
+        return self._ret(o.goals_reached), self._ret(o.violated)
 
     # ---- fused step -------------------------------------------------------------------------------------------
     def step(self, actions, out: Optional[StepOut] = None) -> StepOut:
@@ -334,7 +392,7 @@ class BatchedMapfGym:
             so = _cabi.MapfStepOutHost(status=hb["status"].data_ptr(), reward=hb["reward"].data_ptr(),
                                        cost=hb["cost"].data_ptr(), train_valid=None if tvh is None else tvh.data_ptr(),
                                        goals_reached=hb["goals_reached"].data_ptr(), violated=hb["violated"].data_ptr(),
-                                       shadow_goals=hb["shadow_goals"].data_ptr(), fixed_actions=None)
+                                       shadow_goals=hb["shadow_goals"].data_ptr(), fixed_actions=None, good_actions=None)
             d2h = sum(hb[k].numel() * hb[k].element_size() for k in hb if k not in ("actions", "action_ring", "_slab"))
             cached = (key, so, d2h, _ptr(hb.get("obs")), _ptr(hb.get("vec")))
             self._host_call_cache = cached
@@ -345,6 +403,111 @@ class BatchedMapfGym:
                     "mapf_step_observe_host")
         h2d = act.numel()
         return h2d, d2h
+
+
+    # ---- split-phase host call: step t's results travel to the host while step t+1 computes -------------------------
+    def host_layout(self, with_train_valid: bool = False) -> "_cabi.MapfHostLayout":
+        key = bool(with_train_valid)
+        if key not in self._host_layouts:
+            L = _cabi.MapfHostLayout()
+            _cabi.check(self._lib.mapf_host_layout(self._h, int(key), C.byref(L)), "mapf_host_layout")
+            self._host_layouts[key] = L
+        return self._host_layouts[key]
+
+    def make_host_ring(self, slots: int = 2, action_slots: int = 2, with_train_valid: bool = False, numa_bind: bool = True):
+        """ONE pinned slab holding `slots` result slots (the layout ``mapf_host_layout`` reports: every per-agent result of
+        a step is contiguous, so a step's results come back with one copy) and an int8 [action_slots, W, N] action ring.
+        Returns ``{"slots": [dict of views per slot], "action_ring": ..., "_slab": ...}``.  numa_bind: allocate while the
+        calling thread is bound to the CPUs next to this GPU (first-touch places the pages on the GPU's NUMA node)."""
+        L = self.host_layout(with_train_valid)
+        W, N = self.W, self.N
+        sb = int(L.slot_bytes)
+        act_bytes = (max(1, action_slots) * W * N + 255) // 256 * 256
+        restore = _bind_near_gpu(self.device) if numa_bind else None
+        try:
+            slab = torch.empty((slots * sb + act_bytes,), dtype=torch.uint8, pin_memory=True)
+            slab.zero_()
+        finally:
+            if restore is not None:
+                restore()
+        views = []
+        for k in range(slots):
+            b = slab[k * sb:(k + 1) * sb]
+
+            def f(off, n, dt, shape):
+                return b[off:off + n].view(dt).view(shape)
+            d = dict(reward=f(L.off_reward, W * N * 4, torch.float32, (W, N)), cost=f(L.off_cost, W * N * 4, torch.float32, (W, N)),
+                     shadow_goals=f(L.off_shadow_goals, W * 4, torch.int32, (W,)), status=f(L.off_status, W * N, torch.int8, (W, N)),
+                     goals_reached=f(L.off_goals_reached, W * N, torch.uint8, (W, N)),
+                     violated=f(L.off_violated, W * N, torch.uint8, (W, N)),
+                     fixed_actions=f(L.off_fixed_actions, W * N, torch.int8, (W, N)), _raw=b)
+            if with_train_valid:
+                d["train_valid"] = f(L.off_train_valid, W * N * 20, torch.float32, (W, N, 5))
+            views.append(d)
+        ring = slab[slots * sb:slots * sb + max(1, action_slots) * W * N].view(torch.int8).view(max(1, action_slots), W, N)
+        return {"slots": views, "action_ring": ring, "_slab": slab, "with_train_valid": bool(with_train_valid),
+                "slot_bytes": sb}
+
+    def step_observe_host_begin(self, actions: torch.Tensor, slot: dict, obs_dev: torch.Tensor, vec_dev: torch.Tensor,
+                                train_valid_dev: Optional[torch.Tensor] = None, with_train_valid: bool = False):
+        """Queue one env step for a HOST runner and return immediately: `actions` (int8 [W,N] host tensor, ideally a slice of
+        the ring's pinned slab) -> device, ONE fused step+observe launch into obs_dev / vec_dev, all per-agent results ->
+        `slot` (one of ``make_host_ring()["slots"]``) with ONE device-to-host copy.  ``host_wait(age)`` makes a slot
+        readable.  Returns (h2d_bytes, d2h_bytes)."""
+        assert not actions.is_cuda and actions.dtype == torch.int8 and actions.is_contiguous() and actions.numel() == self.W * self.N
+        tvd = train_valid_dev
+        if with_train_valid and tvd is None:
+            tvd = self._out.train_valid
+        _cabi.check(self._lib.mapf_step_observe_host_begin(self._h, _ptr(actions), C.c_void_p(slot["_raw"].data_ptr()),
+                                                           int(bool(with_train_valid)), _ptr(obs_dev), _ptr(vec_dev),
+                                                           _ptr(tvd), self._stream()), "mapf_step_observe_host_begin")
+        self._eval_key = None
+        return actions.numel(), int(self.host_layout(with_train_valid).slot_bytes)
+
+    def host_wait(self, age: int = 0):
+        """Block until the results of the most recent ``step_observe_host_begin`` (age 0) or the one before (age 1) are in
+        their host slot."""
+        _cabi.check(self._lib.mapf_step_observe_host_wait(self._h, int(age)), "mapf_step_observe_host_wait")
+
+
+def _bind_near_gpu(device):
+    """Bind the calling thread to the CPUs NVML reports as closest to `device`; returns a callable that restores the
+    previous affinity, or None when NVML / the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = device.index or 0
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ent = vis.split(",")[idx].strip()
+            idx = int(ent) if ent.isdigit() else idx
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * k + b for k, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return lambda: os.sched_setaffinity(0, prev)
+    except Exception:
+        return None
+
+
+def checksum_rows(t: torch.Tensor) -> torch.Tensor:
+    """64-bit position-keyed checksum of every row t[r] of a contiguous CUDA tensor of 4-byte-multiple rows
+    (``mapf_checksum_rows``): int64 [rows] holding the uint64 bit patterns."""
+    lib = _cabi.load_library()
+    assert t.is_cuda and t.is_contiguous()
+    rows = int(t.shape[0])
+    row_bytes = (t.numel() // max(rows, 1)) * t.element_size() if rows else 0
+    out = torch.empty((rows,), dtype=torch.int64, device=t.device)
+    stream = C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    with torch.cuda.device(t.device):
+        _cabi.check(lib.mapf_checksum_rows(_ptr(t), rows, row_bytes, _ptr(out), stream), "mapf_checksum_rows")
+    return out
 
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, last_values: torch.Tensor, gamma: float = 0.95,

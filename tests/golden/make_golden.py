@@ -111,7 +111,14 @@ def _draw_world(rng, case, mapf_gym):
         allfree = np.argwhere(free)
         sel = rng.choice(len(cells), size=4, replace=False)
         hseq = [tuple(int(x) for x in cells[s]) for s in sel]
-        perm = rng.permutation(len(allfree))
+        clustered = rng.random() < case.get("cluster", 0.0)
+        if clustered:
+            # agents start packed around the human's start (nearest free cells first, ties shuffled): human collisions
+            # (-2), the -2 -> -3 overwrite of getActionStatus (mapf_gym.py:460-472) and fixActions branch 3 need a crowd
+            d = np.abs(allfree - np.asarray(hseq[0])).sum(1) + rng.random(len(allfree)) * 0.5
+            perm = np.argsort(d, kind="stable")
+        else:
+            perm = rng.permutation(len(allfree))
         starts = []
         for k in perm:
             c = tuple(int(x) for x in allfree[k])
@@ -127,7 +134,10 @@ def _draw_world(rng, case, mapf_gym):
             for q in range(Q):
                 # mostly nearby goals so that arrivals happen within a short trace
                 for _ in range(50):
-                    if rng.random() < case.get("near", 0.7):
+                    if clustered and q == 0 and rng.random() < 0.8:
+                        # first goal next to the human's goal: the crowd walks with the human
+                        cand = (hseq[1][0] + int(rng.integers(-2, 3)), hseq[1][1] + int(rng.integers(-2, 3)))
+                    elif rng.random() < case.get("near", 0.7):
                         cand = (prev[0] + int(rng.integers(-3, 4)), prev[1] + int(rng.integers(-3, 4)))
                     else:
                         cand = tuple(int(x) for x in allfree[rng.integers(len(allfree))])
@@ -281,8 +291,9 @@ def run_case(name, case, seed, out_dir=None):
     hlen = np.zeros((W,), dtype=np.int32)
     tape = np.zeros((W, TL), dtype=np.int8)
     tape_len = np.zeros((W,), dtype=np.int32)
-    bfs0 = np.full((W, N, Hm, Wm), -1, dtype=np.int16)
-    bfsT = np.full((W, N, Hm, Wm), -1, dtype=np.int16)
+    WB = min(W, case.get("bfs_worlds", W))     # BFS maps are the bulk of a fixture: large cases keep the first WB worlds'
+    bfs0 = np.full((WB, N, Hm, Wm), -1, dtype=np.int16)
+    bfsT = np.full((WB, N, Hm, Wm), -1, dtype=np.int16)
     for k, w in enumerate(worlds):
         h, wd = w["obst"].shape
         sizes[k] = (h, wd)
@@ -291,8 +302,9 @@ def run_case(name, case, seed, out_dir=None):
         hlen[k] = w["htrace"].shape[0]
         tape[k, :len(w["tape"])] = w["tape"]
         tape_len[k] = len(w["tape"])
-        bfs0[k, :, :h, :wd] = w["bfs0"]
-        bfsT[k, :, :h, :wd] = w["bfsT"]
+        if k < WB:
+            bfs0[k, :, :h, :wd] = w["bfs0"]
+            bfsT[k, :, :h, :wd] = w["bfsT"]
     sc = Scenario(obst=obst, starts=np.stack([w["starts"] for w in worlds]),
                   goal_queue=np.stack([w["goals"] for w in worlds]), htrace=htrace, hlen=hlen,
                   hp5=np.stack([w["hp5"] for w in worlds]) if worlds[0]["hp5"].ndim == 2 else
@@ -326,7 +338,10 @@ CASES = {
     # BASELINE.json config 2 shape
     "g_20x20_n8": dict(map="density", size=(20, 20), density=(0.2, 0.2), N=8, W=12, T=40, Q=12, seed=2),
     # BASELINE.json config 3 shape
-    "g_40x40_n32": dict(map="density", size=(40, 40), density=(0.0, 0.3), N=32, W=3, T=24, Q=8, seed=3),
+    # BASELINE.json config 3 shape (the headline): 64 worlds x 64 steps, half of them with the agents packed around the
+    # human so that status -2, the -2 -> -3 overwrite and the fixActions tape all occur at this shape
+    "g_40x40_n32": dict(map="density", size=(40, 40), density=(0.0, 0.3), N=32, W=64, T=64, Q=8, seed=3, cluster=0.5,
+                        bfs_worlds=8),
     # crowded: exercises status -3 overwrite and the fixActions tape
     "g_8x8_n8_dense": dict(map="density", size=(8, 8), density=(0.25, 0.3), N=8, W=40, T=30, Q=10, seed=4,
                            greedy=0.6),

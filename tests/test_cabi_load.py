@@ -35,15 +35,17 @@ def test_python_binding_lists_every_symbol(lib_path):
     declared = set(re.findall(r"\b(mapf_[a-z_0-9]+)\s*\(", body))
     assert declared == set(_cabi.EXPORTED)
     lib = _cabi.load_library()
-    assert lib.mapf_abi_version() == 1
+    assert lib.mapf_abi_version() == _cabi.ABI_VERSION == 2
 
 
 def test_config_struct_layout_matches_header():
     from primal_ppo_b200 import _cabi
-    assert ctypes.sizeof(_cabi.MapfConfig) == 12 * 4 + 8 + 2 * 4
+    assert ctypes.sizeof(_cabi.MapfConfig) == 12 * 4 + 8 + 4 * 4
     assert _cabi.MapfConfig.seed.offset == 48
+    assert _cabi.MapfConfig.goal_sampling.offset == 64
     assert ctypes.sizeof(_cabi.MapfScenario) == 9 * 8
-    assert ctypes.sizeof(_cabi.MapfStepOut) == 8 * 8
+    assert ctypes.sizeof(_cabi.MapfStepOut) == 9 * 8
+    assert ctypes.sizeof(_cabi.MapfHostLayout) == 9 * 8
 
 
 def test_null_arguments_are_rejected_without_gpu(lib_path):
@@ -70,13 +72,17 @@ def test_header_is_plain_c_and_links(lib_path, tmp_path):
     import subprocess
     src = tmp_path / "t.c"
     src.write_text('#include "mapf_b200.h"\n#include <stdio.h>\nint main(void) { MapfConfig c; MapfScenario s; MapfStepOut o; '
-                   'MapfGenConfig g; (void)c; (void)s; (void)o; (void)g; printf("%d %d\\n", mapf_abi_version(), mapf_create(0, 0)); return 0; }\n')
+                   'MapfGenConfig g; MapfHostLayout l; (void)c; (void)s; (void)o; (void)g; (void)l; '
+                   'printf("%d %d %d %d %d\\n", mapf_abi_version(), mapf_create(0, 0), (int)sizeof(MapfConfig), (int)sizeof(MapfStepOut), '
+                   '(int)sizeof(MapfHostLayout)); return 0; }\n')
     exe = tmp_path / "t"
     libdir = os.path.dirname(lib_path)
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
                     "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(lib_path), "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
-    assert out == ["1", "-2"]
+    from primal_ppo_b200 import _cabi
+    assert out == ["2", "-2", str(ctypes.sizeof(_cabi.MapfConfig)), str(ctypes.sizeof(_cabi.MapfStepOut)),
+                   str(ctypes.sizeof(_cabi.MapfHostLayout))]
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
