@@ -9,7 +9,10 @@ Workload (N=1) = BASELINE.json configs[2]: 65 536 lockstep 40x40 worlds, 32 agen
 uniform random actions.  Weak scaling: every rank owns 65 536 worlds; worlds never communicate.
 
 Printed JSON (rank 0): value = whole-job agent-steps/s with inputs resident in HBM; `e2e` = the same through the
-host-buffer C-ABI call (actions from pinned host memory, per-agent results read back to the host every step);
+split-phase host-buffer C-ABI call (mapf_step_observe_host_begin/_wait: every step's joint action comes from pinned host
+memory and every step's per-agent results are copied back and read on the host, one step behind the launch);
+`sustained` = the same device-resident loop held for >= 2 s;  `strong` / `fov_sweep` / `ppo` = BASELINE configs[2] with the
+65 536 worlds split over the ranks, configs[4] and configs[3] (all ranks take part, times are max over ranks);
 `roofline` for the dominant kernel (the fused step_observe_kernel) from CUDA events inside the timed region; `cpu_baseline` = the C port
 of the reference's algorithm (oracle/) on this box's host cores.  `--impl reference` times that CPU path alone.
 BENCH_E2E_DEBUG=1 prints the wall time of every e2e call on stderr.
@@ -177,6 +180,201 @@ def build_scenario(worlds, seed):
                            unique_maps=min(256, worlds), fov=FOV, num_channel=CH)
 
 
+def _max_over_ranks(x, dev, world_size):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_env_loop(env, ring, obs, vec, steps, dev, world_size, warmup=3):
+    """`steps` fused env steps, CUDA events on the launching stream, barrier + synchronize on both sides; returns
+    milliseconds (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    for i in range(warmup):
+        env.step_observe(ring[i % len(ring)], obs_out=(obs, vec))
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        env.step_observe(ring[i % len(ring)], obs_out=(obs, vec))
+    b.record()
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    return _max_over_ranks(a.elapsed_time(b), dev, world_size)
+
+
+def bench_strong(sc, dev, rank, world_size, steps):
+    """BASELINE configs[2] as STRONG scaling: 65 536 worlds in total, 65 536 / G per GPU."""
+    import torch
+    from primal_ppo_b200 import BatchedMapfGym
+    total = 65536
+    Wl = total // world_size
+    env = BatchedMapfGym(sc.slice(0, Wl), device=dev, seed=1234, use_tape=False, world_offset=rank * Wl)
+    obs = torch.empty((Wl, N_AGENTS, CH, FOV, FOV), dtype=torch.float32, device=dev)
+    vec = torch.empty((Wl, N_AGENTS, 4), dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(77 + rank)
+    ring = [torch.randint(0, 5, (Wl, N_AGENTS), generator=gen, device=dev, dtype=torch.int8) for _ in range(8)]
+    ms = timed_env_loop(env, ring, obs, vec, steps, dev, world_size, warmup=5)
+    # the same through the split-phase host call (pinned actions in, per-agent results out, read one step behind)
+    hr = env.make_host_ring(slots=2, action_slots=8)
+    for k, r in enumerate(ring):
+        hr["action_ring"][k].copy_(r)
+    for i in range(3):
+        env.step_observe_host_begin(hr["action_ring"][i % 8], hr["slots"][i & 1], obs, vec)
+    env.host_wait(0)
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        env.step_observe_host_begin(hr["action_ring"][i % 8], hr["slots"][(i + 3) & 1], obs, vec)
+        if i > 0:
+            env.host_wait(1)
+            _ = float(hr["slots"][(i + 2) & 1]["reward"][0, 0])
+    env.host_wait(0)
+    torch.cuda.synchronize(dev)
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world_size)
+    out = {"total_worlds": total, "worlds_per_gpu": Wl, "steps": steps, "ms_per_step": ms / steps,
+           "value": total * N_AGENTS * steps / (ms * 1e-3), "e2e_value": total * N_AGENTS * steps / e2e_s,
+           "unit": "agent-steps/s", "scaling": "strong"}
+    del env, obs, vec, ring, hr
+    torch.cuda.empty_cache()
+    return out
+
+
+FOV_SWEEP = ((9, 16384), (15, 8192), (21, 4096), (31, 2048))      # (FOV, worlds per GPU): obs <= ~6 GB per GPU
+
+
+def bench_fov_sweep(dev, rank, world_size, steps=10):
+    """BASELINE configs[4]: 80x80 worlds, 128 agents, FOV 9/15/21/31 (memory-bound roofline stress), worlds generated on
+    the device.  Per FOV: ms per step of mapf_step_observe (max over ranks), algorithmic GB/s and fraction of the peak."""
+    import torch
+    from primal_ppo_b200 import BatchedMapfGym, generate_scenario_device
+    H, N, C = 80, 128, 6
+    peak, _ = measured_peaks()
+    rows = []
+    for F, W in FOV_SWEEP:
+        dsc = generate_scenario_device(W, H, H, N, kind="density", density=(0.0, 0.3), queue_len=8, seed=900 + F,
+                                       world_offset=rank * W, device=dev, fov=F)
+        env = BatchedMapfGym(dsc, device=dev, use_tape=False, world_offset=rank * W)
+        obs = torch.empty((W, N, C, F, F), device=dev); vec = torch.empty((W, N, 4), device=dev)
+        gen = torch.Generator(device=dev); gen.manual_seed(F + rank)
+        ring = [torch.randint(0, 5, (W, N), generator=gen, device=dev, dtype=torch.int8) for _ in range(4)]
+        ms = timed_env_loop(env, ring, obs, vec, steps, dev, world_size) / steps
+        # the two launches separately (local timing)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        env.step(ring[0]); env.getAllObservations(out=(obs, vec)); torch.cuda.synchronize(dev)
+        ev[0].record(); env.step(ring[1]); ev[1].record(); env.getAllObservations(out=(obs, vec)); ev[2].record()
+        torch.cuda.synchronize(dev)
+        _, b_obs, b_all = algorithmic_bytes(N, H, H, C, F)
+        rows.append({"fov": F, "worlds_per_gpu": W, "ms_per_step": ms, "agent_steps_per_s": W * N * world_size / (ms * 1e-3),
+                     "step_observe_gbs": b_all * W * N / (ms * 1e-3) / 1e9, "step_observe_frac": b_all * W * N / (ms * 1e-3) / 1e9 / peak,
+                     "step_ms": ev[0].elapsed_time(ev[1]), "observe_ms": ev[1].elapsed_time(ev[2]),
+                     "observe_frac": b_obs * W * N / (ev[1].elapsed_time(ev[2]) * 1e-3) / 1e9 / peak,
+                     "worlds_with_error_flags": float((env.state()["err"] != 0).float().mean())})
+        del env, obs, vec, ring, dsc
+        torch.cuda.empty_cache()
+    return {"workload": "80x80 worlds, 128 agents, FOV sweep (BASELINE.json configs[4])", "n_gpus": world_size, "rows": rows}
+
+
+def bench_ppo(dev, rank, world_size, worlds=1024, T=256, rows=256, minibatches=8):
+    """BASELINE configs[3]: full PPO rollout + update with the restated net.py policy, the GPU vector env (goals sampled on
+    device), the GAE kernel and ONE NCCL all-reduce of the flat gradient per minibatch (reference: driver.py:76-134,
+    model.py:177-185).  Also checks, over NCCL, that the N-rank gradient of a fixed global minibatch equals the 1-rank
+    gradient of the same minibatch (fp32, TF32 off, dropout off): max |g_N - g_1| / max |g_1|."""
+    import torch
+    import torch.distributed as dist
+    from primal_ppo_b200 import BatchedMapfGym, generate_scenario_device
+    from primal_ppo_b200.ppo import PPOConfig, ScrimpPolicy, VecPPOTrainer
+    group = dist.group.WORLD if world_size > 1 else None
+    N = N_AGENTS
+    dsc = generate_scenario_device(worlds, H, WD, N, kind="density", density=(0.0, 0.3), queue_len=1, seed=4242,
+                                   world_offset=rank * worlds, device=dev)
+    env = BatchedMapfGym(dsc, device=dev, seed=1234, use_tape=False, world_offset=rank * worlds, goal_sampling=True)
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    pol = ScrimpPolicy().to(dev).use_channels_last()
+    cfg = PPOConfig(n_steps=T, n_epochs=1)
+    tr = VecPPOTrainer(env, pol, cfg, group=group, amp_dtype=torch.bfloat16, rows_per_minibatch=rows, seed=1234 + rank)
+
+    def sync():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    # warm-up: a few policy forwards + env steps (cuDNN autotune, allocator), then one timed full rollout
+    b = tr.buf
+    for t in range(3):
+        tr._forward(b.obs[0], b.vec[0], b.ps[0], b.values[0], b.cost_values[0])
+    sync()
+    t0 = time.perf_counter(); perf = tr.collect(); sync()
+    t_roll = _max_over_ranks(time.perf_counter() - t0, dev, world_size)
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for t in range(T):
+        env.step_observe(b.actions[t], obs_out=(b.obs[t + 1], b.vec[t + 1]))
+    e.record(); torch.cuda.synchronize(dev)
+    env_ms = a.elapsed_time(e) / T
+    tr.update(perf, max_minibatches=2)                     # warm-up
+    sync()
+    t0 = time.perf_counter(); stats = tr.update(perf, max_minibatches=minibatches); sync()
+    t_upd = _max_over_ranks(time.perf_counter() - t0, dev, world_size)
+    out = {"workload": f"PPO rollout+update (BASELINE.json configs[3]): {worlds} worlds/GPU 40x40, {N} agents, T={T}, goals sampled on "
+                       f"device, ScrimpPolicy {tr.learner.flat_grad.numel()} params bf16 autocast, minibatch {rows} rows x {N} agents per GPU",
+           "n_gpus": world_size, "rollout_agent_steps_per_s": worlds * N * T * world_size / t_roll,
+           "rollout_ms_per_step": 1e3 * t_roll / T, "env_ms_per_step": env_ms,
+           "update_agent_rows_per_s": rows * N * len(stats) * world_size / t_upd, "update_ms_per_minibatch": 1e3 * t_upd / len(stats),
+           "rollout_plus_update_agent_steps_per_s": worlds * N * T * world_size / (t_roll + t_upd * (T * worlds // rows) / len(stats)),
+           "note_rollout_plus_update": "one rollout + ONE epoch over all its rows, the update time extrapolated from the timed minibatches",
+           "grad_bytes": tr.learner.flat_grad.numel() * 4, "episode_perf": perf, "last_stats": stats[-1]}
+    if world_size > 1:
+        a.record()
+        for _ in range(10):
+            dist.all_reduce(tr.learner.flat_grad)
+        e.record(); torch.cuda.synchronize(dev)
+        out["grad_allreduce_ms"] = _max_over_ranks(a.elapsed_time(e) / 10, dev, world_size)
+        out["grad_allreduce_gbs"] = out["grad_bytes"] / (out["grad_allreduce_ms"] * 1e-3) / 1e9
+        # ---- N-rank gradient vs 1-rank gradient on the same global minibatch, over NCCL --------------------------------
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        lr_, amp = tr.learner, tr.learner.amp_dtype
+        pol.eval(); lr_.amp_dtype = None
+        try:
+            per = max(1, 256 // world_size)                # reference MINIBATCH_SIZE rows in total
+            g = torch.Generator(device=dev); g.manual_seed(5 + rank)
+            mine = b.minibatch(torch.randperm(T * worlds, generator=g, device=dev)[:per])
+            full = {}
+            for k, v in mine.items():
+                parts = [torch.empty_like(v) for _ in range(world_size)]
+                dist.all_gather(parts, v.contiguous())
+                full[k] = torch.cat(parts)
+            lr_.compute_gradients(mine)                    # shard gradient + NCCL all-reduce
+            g_n = lr_.flat_grad.clone()
+            lr_.group = None
+            lr_.compute_gradients(full)                    # the same global minibatch on one rank
+            g_1 = lr_.flat_grad.clone()
+            lr_.group = group
+            d = torch.stack([(g_n - g_1).abs().max(), g_1.abs().max()])
+            dist.all_reduce(d, op=dist.ReduceOp.MAX)
+            tol = 2e-4
+            out["grad_check"] = {"global_minibatch_rows": per * world_size, "max_abs_diff": float(d[0]), "max_abs_grad": float(d[1]),
+                                 "rel": float(d[0] / d[1]), "tolerance_rel": tol, "ok": bool(float(d[0]) <= tol * float(d[1])),
+                                 "how": "fp32, TF32 off, dropout off; N-rank = shard losses as shares of the global mean + one NCCL "
+                                        "all-reduce of the flat gradient; 1-rank = the all-gathered minibatch on one GPU"}
+        finally:
+            pol.train(); lr_.amp_dtype = amp; lr_.group = group
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    del tr, env, pol, dsc
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_port_throughput(budget_s, worlds, threads, seed=7):
     """agent-steps/s of the oracle (C port of the reference's algorithm) on the host cores: the reference's 5-call step
     + getAllObservations on the same kind of worlds and actions, for ~budget_s seconds."""
@@ -248,6 +446,10 @@ def main():
     ap.add_argument("--worlds", type=int, default=65536, help="worlds per GPU")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the configs[3] PPO rollout+update extra")
+    ap.add_argument("--ppo-worlds", type=int, default=1024, help="worlds per GPU of the PPO extra")
+    ap.add_argument("--ppo-steps", type=int, default=256, help="rollout length T of the PPO extra")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -281,28 +483,49 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    hb = env.make_host_buffers(with_obs=False, action_slots=8)     # one pinned slab: results + the runner's action ring
+    ring_h = env.make_host_ring(slots=2, action_slots=8)            # ONE pinned slab: 2 result slots + the runner's action ring
     for k, r in enumerate(ring):
-        hb["action_ring"][k].copy_(r)
-    host_ring = [hb["action_ring"][k] for k in range(8)]
+        ring_h["action_ring"][k].copy_(r)
+    host_ring = [ring_h["action_ring"][k] for k in range(8)]
 
     def run_e2e(n_calls):
-        """n_calls of the host-buffer C-ABI call, wall clock, after 3 untimed calls.  Returns (seconds, h2d, d2h bytes)."""
+        """n_calls env steps through the split-phase host call, wall clock, after 3 untimed calls.  Every step: the joint
+        action is read from pinned host memory (H2D inside the call), ONE fused launch, the step's per-agent results come
+        back with one D2H copy and are READ ON THE HOST — one step behind the launch, which is how a rollout loop consumes
+        them (runner.py:84-99 only appends them).  Returns (seconds, h2d bytes, d2h bytes per step)."""
         for i in range(3):
-            env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])
+            env.step_observe_host_begin(host_ring[i % 8], ring_h["slots"][i & 1], obs, vec)
+        env.host_wait(0)
         barrier()
         t0 = time.perf_counter()
         stamps = []
+        sink = 0.0
         for i in range(n_calls):
-            h2d_, d2h_ = env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])   # the runner's pinned host action array
-            _ = float(hb["reward"][0, 0])                            # the step's result is read on the host
+            h2d_, d2h_ = env.step_observe_host_begin(host_ring[i % 8], ring_h["slots"][(i + 3) & 1], obs, vec)
+            if i > 0:
+                env.host_wait(1)                                         # step i-1 has landed while step i runs
+                sink += float(ring_h["slots"][(i + 2) & 1]["reward"][0, 0])
             stamps.append(time.perf_counter())
+        env.host_wait(0)
+        sink += float(ring_h["slots"][(n_calls + 2) & 1]["reward"][0, 0])
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if os.environ.get("BENCH_E2E_DEBUG"):
             d = [round((b - a) * 1e3, 3) for a, b in zip([t0] + stamps[:-1], stamps)]
             print("e2e per-call ms:", d, "mean", round(dt / n_calls * 1e3, 3), file=sys.stderr)
         return dt, h2d_, d2h_
+
+    def run_e2e_sync(n_calls):
+        """The synchronous form (mapf_step_observe_host: results on the host before the call returns)."""
+        hb = env.make_host_buffers(with_obs=False)
+        for i in range(3):
+            env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(n_calls):
+            env.step_observe_host(hb, obs, vec, actions=host_ring[i % 8])
+            _ = float(hb["reward"][0, 0])
+        return time.perf_counter() - t0
 
     # ---------------- device-resident throughput (value): one fused step+observe launch per step ------------------
     clk = ClockSampler(local_rank).start()          # running before the warm-up so that it has samples in the timed region
@@ -352,8 +575,46 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = Wn * N * Ke * world_size / float(te.item())
 
+    # ---------------- the same device-resident loop held for >= 2 s (does the 20-step number survive?) -------------
+    sustained = None
+    if not args.no_extras:
+        n_sus = int(max(200, args.sustained_seconds * 1e3 / max(fused_ms, 1e-3)))
+        clk2 = ClockSampler(local_rank).start()
+        barrier()
+        with clk2:
+            sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sa.record()
+            for i in range(n_sus):
+                env.step_observe(ring[i % 8], obs_out=(obs, vec))
+            sb.record()
+            barrier()
+        sus_ms = _max_over_ranks(sa.elapsed_time(sb), dev, world_size)
+        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                     "value": Wn * N * n_sus * world_size / (sus_ms * 1e-3), "unit": "agent-steps/s", "clocks": clk2.summary()}
+
+    # ---------------- extras every rank takes part in: strong scaling, configs[4], configs[3] ------------------------
+    multi = {}
+    if not args.no_extras:
+        for name, fn in (("strong", lambda: bench_strong(sc, dev, rank, world_size, max(K, 50))),
+                         ("fov_sweep", lambda: bench_fov_sweep(dev, rank, world_size)),
+                         ("ppo", lambda: bench_ppo(dev, rank, world_size, worlds=args.ppo_worlds, T=args.ppo_steps))):
+            if name == "ppo" and args.no_ppo:
+                continue
+            try:
+                multi[name] = fn()
+            except Exception as ex:                      # an extra must never take the headline line down with it
+                import traceback
+                traceback.print_exc()
+                multi[name] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+                torch.cuda.empty_cache()
+
     line_extra = {}
     if rank == 0 and not args.no_extras:
+        try:
+            line_extra["e2e_synchronous_call"] = {"value": Wn * N * 10 / run_e2e_sync(10), "unit": "agent-steps/s (1 GPU)",
+                                                  "note": "mapf_step_observe_host: results on the host before the call returns"}
+        except Exception as ex:
+            line_extra["e2e_synchronous_call"] = {"error": str(ex)[:200]}
         # observations copied to host as well (what the reference's getAllObservations returns): PCIe-bound
         try:
             hbo = env.make_host_buffers(with_obs=True)
@@ -481,10 +742,11 @@ def main():
                            "worlds_with_error_flags": err_frac},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": Ke, "note": "mapf_step_observe_host: actions from pinned host memory; per-agent step results "
-                                             "(status, reward, cost, goals, violations, shadow goals) copied back to pinned host "
-                                             "memory every step; observations and trainValid stay in HBM as the policy's / learner's "
-                                             "input tensors"},
+                        "steps": Ke, "note": "mapf_step_observe_host_begin/_wait (split-phase): every step the joint action comes "
+                                             "from pinned host memory (H2D), ONE fused launch, and ALL per-agent results (status, "
+                                             "reward, cost, goals reached, violations, shadow goals, executed actions) return in one "
+                                             "D2H copy of a contiguous slab and are read on the host one step behind the launch; "
+                                             "observations and trainValid stay in HBM as the policy's / learner's input tensors"},
                 "gpu_launches": K,
                 "roofline": {"bound": "hbm", "kernel": "step_observe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": ncu_traffic("step_observe_kernel"), "peak_source": peak_src,
@@ -503,6 +765,9 @@ def main():
                             "note": "step_kernel / observe_kernel: the same work as two launches (mapf_step, mapf_observe), "
                                     "timed in a separate loop of %d steps" % Kk},
                 "cpu_baseline": cpu}
+        if sustained is not None:
+            line["sustained"] = sustained
+        line.update(multi)
         line.update(line_extra)
         print(json.dumps(line), flush=True)
     if world_size > 1:

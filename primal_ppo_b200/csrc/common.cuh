@@ -240,6 +240,9 @@ cudaError_t launch_observe(const EnvView &v, float *obs, float *vec, int *work_c
 bool step_observe_fusable(const EnvView &v);
 cudaError_t launch_step_observe(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
                                 int *work_counter, cudaStream_t s, int out_bf16 = 0);
+bool step_observe_wide_fusable(const EnvView &v);
+cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
+                                     int *work_counter, cudaStream_t s, int out_bf16 = 0);
 cudaError_t launch_observe_wide(const EnvView &v, float *obs, float *vec, int *work_counter, cudaStream_t s, int out_bf16 = 0);
 cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n, const int32_t *n_dev, int16_t *out,
                        int scatter, int *work_counter, cudaStream_t s);

@@ -251,6 +251,20 @@ static cudaError_t do_step(MapfEnv *e, const int8_t *actions, const int8_t *stat
     return launch_step_wide(e->v, actions, status, o, mode, s);
 }
 
+// One env step of the rollout loop: the warp-per-world fused kernel (N <= 32, one observation chunk), else the
+// CTA-per-world fused kernel (N <= 128), else the two launches back to back.  MAPF_DBG_FLAGS bit 0 forces the two launches.
+static cudaError_t do_step_observe(MapfEnv *e, const int8_t *actions, const MapfStepOut &o, float *obs, float *vec,
+                                   cudaStream_t s, int out_bf16) {
+    const EnvView &v = e->v;
+    if (!(v.dbg_flags & 1)) {
+        if (step_observe_fusable(v)) return launch_step_observe(v, actions, o, obs, vec, WC(e, WC_FUSED), s, out_bf16);
+        if (step_observe_wide_fusable(v)) return launch_step_observe_wide(v, actions, o, obs, vec, WC(e, WC_FUSED_WIDE), s, out_bf16);
+    }
+    cudaError_t err = do_step(e, actions, nullptr, o, MODE_FUSED, s);
+    if (err != cudaSuccess) return err;
+    return launch_observe(v, obs, vec, WC(e, WC_OBSERVE), s, out_bf16);
+}
+
 int mapf_evaluate(MapfEnv *e, const int8_t *actions, const MapfStepOut *out, void *stream) {
     NEED_ENV("mapf_evaluate");
     if (!actions || !out) return fail(MAPF_E_NULL, "mapf_evaluate: null argument");
@@ -292,13 +306,7 @@ int mapf_step_observe(MapfEnv *e, const int8_t *actions, const MapfStepOut *out,
     if (int rc = check_vec(vec, "mapf_step_observe")) return rc;
     if (!actions || !out || !obs || !vec) return fail(MAPF_E_NULL, "mapf_step_observe: null argument");
     if (int rc = check_step_n(e, "mapf_step_observe")) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (step_observe_fusable(e->v) && !(e->v.dbg_flags & 1)) {
-        CU(launch_step_observe(e->v, actions, *out, obs, vec, WC(e, WC_FUSED), s));
-    } else {
-        CU(do_step(e, actions, nullptr, *out, MODE_FUSED, s));
-        CU(launch_observe(e->v, obs, vec, WC(e, WC_OBSERVE), s));
-    }
+    CU(do_step_observe(e, actions, *out, obs, vec, (cudaStream_t)stream, 0));
     return MAPF_OK;
 }
 
@@ -316,14 +324,7 @@ int mapf_step_observe_bf16(MapfEnv *e, const int8_t *actions, const MapfStepOut 
     if (int rc = check_vec(vec, "mapf_step_observe_bf16")) return rc;
     if (!actions || !out || !obs_bf16 || !vec) return fail(MAPF_E_NULL, "mapf_step_observe_bf16: null argument");
     if (int rc = check_step_n(e, "mapf_step_observe_bf16")) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    float *obs = reinterpret_cast<float *>(obs_bf16);
-    if (step_observe_fusable(e->v) && !(e->v.dbg_flags & 1)) {
-        CU(launch_step_observe(e->v, actions, *out, obs, vec, WC(e, WC_FUSED), s, 1));
-    } else {
-        CU(do_step(e, actions, nullptr, *out, MODE_FUSED, s));
-        CU(launch_observe(e->v, obs, vec, WC(e, WC_OBSERVE), s, 1));
-    }
+    CU(do_step_observe(e, actions, *out, reinterpret_cast<float *>(obs_bf16), vec, (cudaStream_t)stream, 1));
     return MAPF_OK;
 }
 
@@ -524,12 +525,7 @@ int mapf_step_observe_host_begin(MapfEnv *e, const int8_t *actions_host, void *r
     if (int rc = queue_actions(e, k, actions_host, s)) return rc;
     MapfStepOut o = slot_ptrs(e, k);
     o.train_valid = train_valid_dev;
-    if (step_observe_fusable(v) && !(v.dbg_flags & 1)) {
-        CU(launch_step_observe(v, e->d_actions[k], o, obs_dev, vec_dev, WC(e, WC_FUSED), s));
-    } else {
-        CU(do_step(e, e->d_actions[k], nullptr, o, MODE_FUSED, s));
-        CU(launch_observe(v, obs_dev, vec_dev, WC(e, WC_OBSERVE), s));
-    }
+    CU(do_step_observe(e, e->d_actions[k], o, obs_dev, vec_dev, s, 0));
     CU(cudaEventRecord(e->ev_step[k], s));
     CU(cudaStreamWaitEvent(cs, e->ev_step[k], 0));
     CU(cudaMemcpyAsync(result_slot_host, e->d_slot[k], (size_t)e->lay.slot_bytes, cudaMemcpyDeviceToHost, cs));   // ONE copy

@@ -1,0 +1,166 @@
+// step_observe_wide.cu — one launch for the rollout loop's whole per-step env work (runner.py:64-100) for worlds that do
+// not fit the warp-per-world fused kernel (step_observe.cu): more than 32 agents, or an observation block that needs
+// several chunks (BASELINE.json configs[4]: 80x80 worlds, 128 agents, FOV 9..31).
+//
+// Mapping: ONE persistent CTA of 8 warps per world at a time (worlds are claimed dynamically).  The world is staged once
+// for both phases — padded obstacle bit rows, agent-id grid — then
+//   phase A: joint-step resolution by the whole CTA (step_wide_world.cuh: per-agent work spread over 256 threads, the
+//            order-dependent parts on thread 0 / warp 0),
+//   phase B: the post-step cells and goals go from shared memory straight into the observation build (no state re-read);
+//            the eight warps take chunks of agents round-robin and stream the f32 block out (observe_world.cuh).
+// With two or three CTAs resident per SM the latency-bound phase A of one world hides under the store-bound phase B of
+// the others, which two back-to-back launches (step_wide_kernel, observe_wide_kernel) cannot do: at 80x80x128 / FOV 9 the
+// two launches ran at 0.795 of the HBM roofline against 1.02 for the observation kernel alone.
+// Results are bit-identical to mapf_step followed by mapf_observe.
+#include "common.cuh"
+#include "observe_world.cuh"
+#include "step_wide_world.cuh"
+
+namespace mapf {
+
+namespace {
+
+using namespace ow;
+using namespace sww;
+
+constexpr int FW_WARPS = 8;
+
+template <int C_T, int F_T, bool VEC4>
+__global__ void __launch_bounds__(FW_WARPS * 32)
+step_observe_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, const MapfStepOut out, float *__restrict__ obs,
+                         float *__restrict__ vec, const ObsLayout L, const int shared_bytes, const int scratch_off,
+                         const int per_warp, int *__restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint4 lut[16];
+    __shared__ int s_world;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int N = v.N, P = v.P, GS = v.GS, RW = v.RW, HP = v.HP, nob = v.HP * v.RW;
+    ObsSmem m;
+    m.obits = reinterpret_cast<uint32_t *>(smem_raw);
+    m.abits = reinterpret_cast<uint32_t *>(smem_raw + L.off_abits);
+    m.grid = smem_raw + L.off_grid;
+    m.sgoal = reinterpret_cast<uint32_t *>(smem_raw + L.off_goal);
+    m.spos = m.sgoal + N;
+    unsigned char *mine = smem_raw + shared_bytes + (size_t)warp * per_warp;
+    m.aw = reinterpret_cast<uint32_t *>(mine);
+    m.wb = reinterpret_cast<uint32_t *>(mine + ((size_t)L.CH * L.AST * 4 + 15) / 16 * 16);
+    WideSmem s;
+    s.obits = m.obits;
+    s.grid = m.grid;
+    carve_scratch(s, smem_raw + scratch_off);
+    if (tid < 16) {
+        const uint32_t one = 0x3f800000u, t = tid;
+        lut[t] = make_uint4((t & 1u) ? one : 0u, (t & 2u) ? one : 0u, (t & 4u) ? one : 0u, (t & 8u) ? one : 0u);
+    }
+    for (int k = tid; k < nob; k += blockDim.x) m.abits[k] = 0;
+    for (int k = tid; k < (HP * GS) / 16; k += blockDim.x) reinterpret_cast<uint4 *>(m.grid)[k] = make_uint4(0, 0, 0, 0);
+    const int nchunks = (N + L.CH - 1) / L.CH;
+    for (;;) {
+        __syncthreads();                                   // previous world fully written, grid / abits clean
+        if (tid == 0) s_world = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int w = s_world;
+        if (w >= v.W) break;
+        expand_obstacle_rows(m.obits, v.obst_pack + (size_t)w * v.PW, v, tid, blockDim.x);
+        int rows = v.H, cols = v.Wd;
+        if (v.use_da | v.use_hp) { if (v.dims) { rows = v.dims[2 * w]; cols = v.dims[2 * w + 1]; } }
+        __syncthreads();
+        // ---- phase A: the joint step, by the whole CTA ----------------------------------------------------------------------
+        int nr, nc;                                        // human.getNextPos() after the tick
+        step_wide_world<MODE_FUSED, true>(v, actions, nullptr, out, s, w, tid, blockDim.x, nr, nc);
+        // ---- hand the post-step world to the observation build ---------------------------------------------------------------
+        for (int i = tid; i < N; i += blockDim.x) {
+            const uint32_t pw = s.npos[i];
+            const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
+            m.grid[(r + P) * GS + c + P] = (uint8_t)(i + 1);
+            atomicOr(&m.abits[(r + P) * RW + ((c + P) >> 5)], 1u << ((c + P) & 31));
+            m.sgoal[i] = s.goal[i];
+            m.spos[i] = pw;
+        }
+        __syncthreads();
+        // ---- phase B: chunks of agents, round-robin over the warps -----------------------------------------------------------
+        for (int k = warp; k < nchunks; k += FW_WARPS) {
+            const int c0 = k * L.CH;
+            observe_chunk<C_T, F_T, VEC4>(v, L, m, lut, w, lane, c0, min(L.CH, N - c0), nr, nc, rows, cols, obs, vec);
+        }
+        __syncthreads();
+        for (int i = tid; i < N; i += blockDim.x) {        // un-scatter: the next world starts from a clean grid
+            const uint32_t pw = m.spos[i];
+            const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
+            m.grid[(r + P) * GS + c + P] = 0;
+            m.abits[(r + P) * RW + ((c + P) >> 5)] = 0;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {                                        // the last CTA to finish re-arms the counter
+        const int d = atomicAdd(work_counter + 1, 1);
+        if (d == (int)gridDim.x - 1) { work_counter[0] = 0; work_counter[1] = 0; }
+    }
+}
+
+struct WidePlan {
+    ObsLayout L;
+    int shared_bytes, scratch_off, per_warp;
+    size_t smem;
+    bool ok;
+};
+
+WidePlan make_plan(const EnvView &v, int out_bf16) {
+    WidePlan p;
+    p.ok = false;
+    const int PB = v.C * v.F * v.F;
+    // chunk size: per-warp scratch (aw + wb) of at most ~12 KB, and at least one chunk per warp when N allows it
+    int CH = 32;
+    while (CH > 2 && ((size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 12 * 1024 || (v.N + CH - 1) / CH < FW_WARPS)) CH >>= 1;
+    if ((size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 28 * 1024) return p;
+    p.L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
+    p.L.alias = 0;
+    p.L.out_bf16 = out_bf16;
+    // [obits | abits | grid | goals + cells] shared by the CTA, then the per-warp observation scratch (aw, wb).  The step
+    // phase's scratch is dead once the post-step cells / goals have been handed over, and the observation scratch is dead
+    // during the step phase: they overlay each other (a __syncthreads separates the two uses).
+    p.shared_bytes = (int)(p.L.off_goal + (((size_t)v.N * 8 + 15) / 16) * 16);
+    p.scratch_off = p.shared_bytes;
+    p.per_warp = (int)((((size_t)CH * p.L.AST * 4 + 15) / 16) * 16 + (((size_t)p.L.WB * 4 + 15) / 16) * 16);
+    const size_t obs_scratch = (size_t)p.per_warp * FW_WARPS, step_scratch = al16(scratch_bytes());
+    p.smem = (size_t)p.shared_bytes + (obs_scratch > step_scratch ? obs_scratch : step_scratch);
+    p.ok = p.smem <= 200 * 1024;
+    return p;
+}
+
+}  // namespace
+
+// Shapes served by the CTA-per-world fused kernel: anything the joint step supports (N <= 128) whose staging fits.
+bool step_observe_wide_fusable(const EnvView &v) {
+    if (v.N > NMAX) return false;
+    return make_plan(v, 0).ok;
+}
+
+cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
+                                     int *work_counter, cudaStream_t stream, int out_bf16) {
+    const WidePlan p = make_plan(v, out_bf16);
+    if (!p.ok) return cudaErrorNotSupported;
+    const int PB = v.C * v.F * v.F;
+    const size_t al = out_bf16 ? 8 : 4;
+    const bool vec4 = ((size_t)p.L.CH * PB) % al == 0 && ((size_t)v.N * PB) % al == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e;
+#define LAUNCH(...)                                                                                                \
+    do {                                                                                                           \
+        e = cudaFuncSetAttribute(step_observe_wide_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);  \
+        if (e != cudaSuccess) return e;                                                                            \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_observe_wide_kernel<__VA_ARGS__>, FW_WARPS * 32, p.smem);     \
+        if (per_sm < 1) per_sm = 1;                                                                                \
+        const int blocks = v.W < sms * per_sm ? v.W : sms * per_sm;                                                \
+        step_observe_wide_kernel<__VA_ARGS__><<<blocks, FW_WARPS * 32, p.smem, stream>>>(v, actions, out, obs, vec, p.L, p.shared_bytes, \
+                                                                                          p.scratch_off, p.per_warp, work_counter); \
+    } while (0)
+    if (v.C == 6 && v.F == 9) { if (vec4) LAUNCH(6, 9, true); else LAUNCH(6, 9, false); }
+    else { if (vec4) LAUNCH(0, 0, true); else LAUNCH(0, 0, false); }
+#undef LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace mapf

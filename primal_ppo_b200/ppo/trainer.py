@@ -62,9 +62,16 @@ class PPOLearner:
         self.lagrange.update(episode_cost / n_agents)                # model.py:180
         gn = self.flat_grad.norm()                                   # clip_grad_norm_ over all parameters (:182)
         stats["grad_norm"] = float(gn)
+        stats["lagrangian"] = self.lagrange.value()
+        if not torch.isfinite(gn):
+            # the reference's GradScaler skips a step whose gradients are inf / NaN (model.py:178-186); without this
+            # guard one bad minibatch would poison Adam's moments and the weights for good.  The all-reduced gradient is
+            # the same on every rank, so every rank skips together.
+            self.skipped_steps = getattr(self, "skipped_steps", 0) + 1
+            stats["skipped"] = 1.0
+            return stats
         self.flat_grad.mul_(torch.clamp(self.cfg.max_grad_norm / (gn + 1e-6), max=1.0))
         self.opt.step()
-        stats["lagrangian"] = self.lagrange.value()
         return stats
 
     # ---- checkpoints in the reference's layout (driver.py:164-208) ---------------------------------------------------
@@ -77,7 +84,7 @@ class PPOLearner:
     def load_checkpoint(self, path: str, load_optimizer: bool = True) -> dict:
         """Loads a checkpoint written by `save_checkpoint` OR by the reference (`driver.py:189-194`).  The reference's Adam
         state is indexed by ITS parameter order and is therefore only restored from checkpoints written here."""
-        ck = torch.load(path, map_location=self.flat_grad.device, weights_only=False)
+        ck = torch.load(path, map_location=self.flat_grad.device, weights_only=True)   # tensors / dicts / scalars only
         self.policy.load_reference_state_dict(ck["model"])
         if load_optimizer and "lagrange" in ck:
             self.opt.load_state_dict(ck["optimizer"])
@@ -206,19 +213,29 @@ class VecPPOTrainer:
                     agentCollide=float((b.status == -3).sum(dim=(0, 2), dtype=torch.float32).mean()),
                     shadowGoals=float(b.shadow_goals.sum(dim=0, dtype=torch.float32).mean()))
         if self.group is not None:
+            # mean over ALL worlds of the job: ranks may own different numbers of worlds (shard_range), so the per-rank
+            # means are weighted by the rank's world count
             keys = sorted(perf)
-            t = torch.tensor([perf[k] for k in keys], dtype=torch.float64, device=env.device)
+            t = torch.tensor([perf[k] * env.W for k in keys] + [float(env.W)], dtype=torch.float64, device=env.device)
             dist.all_reduce(t, group=self.group)
-            perf = {k: float(v) / dist.get_world_size(self.group) for k, v in zip(keys, t)}
+            perf = {k: float(v) / float(t[-1]) for k, v in zip(keys, t[:-1])}
         return perf
 
     def update(self, perf: Dict[str, float], max_minibatches: Optional[int] = None):
         """`driver.py:121-131`: n_epochs shuffled passes over the rollout rows."""
         rows_total = self.T * self.env.W
+        per_epoch = rows_total // self.rows_per_minibatch
+        if self.group is not None:
+            # every minibatch issues collectives (advantage statistics, gradient all-reduce): all ranks must run the SAME
+            # number of them even when shard_range gave some ranks one world more than others
+            t = torch.tensor([per_epoch], dtype=torch.int64, device=self.env.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            per_epoch = int(t.item())
         stats, done = [], 0
         for _ in range(self.cfg.n_epochs):
             perm = torch.randperm(rows_total, generator=self.gen, device=self.env.device)
-            for lo in range(0, rows_total - self.rows_per_minibatch + 1, self.rows_per_minibatch):
+            for mb in range(per_epoch):
+                lo = mb * self.rows_per_minibatch
                 batch = self.buf.minibatch(perm[lo:lo + self.rows_per_minibatch])
                 stats.append(self.learner.train_minibatch(batch, perf["episodeCostReward"], self.env.N))
                 done += 1

@@ -287,3 +287,34 @@ def test_gpu_fresh_outputs_do_not_alias():
     for t in range(4):
         assert torch.equal(kept_f[t], truth[t])
     assert kept_a[0].data_ptr() == kept_a[3].data_ptr()
+
+
+@pytest.mark.parametrize("shape", [(48, 80, 80, 128, 9, 24), (64, 16, 16, 48, 9, 32), (24, 80, 80, 128, 15, 12), (12, 80, 80, 128, 21, 8),
+                                   (8, 80, 80, 128, 31, 8), (6, 128, 128, 128, 31, 6), (16, 40, 40, 32, 31, 12), (40, 33, 65, 33, 9, 16),
+                                   (300, 24, 24, 64, 3, 16)])
+def test_gpu_fused_wide_step_observe_matches_oracle(shape):
+    """step_observe_wide_kernel (CTA per world: N > 32, or an observation block that needs several chunks) against the
+    oracle every step, and against the two separate launches (mapf_step + mapf_observe) for every output and the state."""
+    from test_gpu_parity import _run_vs_oracle
+    W, H, Wd, N, F, T = shape
+    dens = (0.1, 0.25) if H <= 24 else (0.0, 0.3)
+    sc = random_scenario(W, H, Wd, N, density=dens, queue_len=4, seed=W + N + F, fov=F, unique_maps=min(W, 16))
+    env, orc = _run_vs_oracle(sc, T=T, fused=True)
+    e2 = _env(sc, seed=1234, use_tape=False)
+    acts = random_actions(T, W, N, seed=1234)
+    for t in range(T):
+        e2.step(torch.from_numpy(acts[t]))
+    s1, s2 = env.state(), e2.state()
+    assert all(torch.equal(s1[k], s2[k]) for k in s1)
+    assert torch.equal(env.counters(), e2.counters())
+    a, b = env.human(), e2.human()
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_gpu_fused_wide_eval_channels():
+    """use_da / use_hp (eval-only channels, per-world dims) through the CTA-per-world fused kernel."""
+    from test_gpu_parity import _run_vs_oracle
+    sc = random_scenario(10, 80, 80, 128, density=(0.0, 0.3), queue_len=3, seed=77, fov=15, use_da=True, use_hp=True)
+    _run_vs_oracle(sc, T=8, fused=True)
+    sc = random_scenario(10, 20, 30, 40, density=(0.0, 0.2), queue_len=3, seed=78, fov=9, use_da=True, use_hp=True, num_channel=6)
+    _run_vs_oracle(sc, T=12, fused=True)

@@ -85,3 +85,63 @@ def test_two_rank_gradient_equals_single_process():
         p.join(timeout=60)
     assert all(ok.values()), ok
     assert all(p.exitcode == 0 for p in procs)
+
+
+class _StubEnv:
+    """Just enough of BatchedMapfGym for VecPPOTrainer.update(): shapes and a device (the rollout buffer is filled by hand)."""
+    def __init__(self, W, N):
+        self.W, self.N, self.C, self.F, self.device = W, N, 6, 9, torch.device("cpu")
+
+    def getAllObservations(self, out=None):
+        out[0].zero_(); out[1].zero_()
+        return out
+
+
+def _run_unequal(rank, world_size, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from primal_ppo_b200.ppo import PPOConfig, ScrimpPolicy
+    from primal_ppo_b200.ppo.trainer import VecPPOTrainer
+    from primal_ppo_b200.shard import shard_range
+    lo, hi = shard_range(5, rank, world_size)              # 5 worlds over 2 ranks: 3 + 2
+    W, T = hi - lo, 2
+    torch.manual_seed(7)
+    pol = ScrimpPolicy().eval()
+    tr = VecPPOTrainer(_StubEnv(W, N), pol, PPOConfig(n_steps=T, n_epochs=2), group=dist.group.WORLD, rows_per_minibatch=2,
+                       seed=3 + rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    b = tr.buf
+    b.obs.copy_((torch.rand(b.obs.shape, generator=g) < 0.2).float()); b.vec.copy_(torch.randn(b.vec.shape, generator=g))
+    b.actions.copy_(torch.randint(0, 5, b.actions.shape, generator=g).to(torch.int8))
+    b.ps.copy_(torch.softmax(torch.randn(b.ps.shape, generator=g), -1))
+    for name in ("values", "cost_values", "rewards", "cost_rewards"):
+        getattr(b, name).copy_(torch.randn(getattr(b, name).shape, generator=g))
+    b.train_valid.copy_((torch.rand(b.train_valid.shape, generator=g) < 0.7).float())
+    b.returns = torch.randn(b.values.shape, generator=g); b.cost_returns = torch.randn(b.values.shape, generator=g)
+    # rank 0 has 6 (time, world) rows = 3 minibatches per epoch, rank 1 has 4 rows = 2: both must run 2 per epoch
+    stats = tr.update(dict(episodeCostReward=1.0))
+    flat_p = torch.cat([p.detach().flatten() for p in tr.learner.params])
+    other = [torch.zeros_like(flat_p) for _ in range(world_size)]
+    dist.all_gather(other, flat_p)
+    if rank == 0:
+        ret.put(dict(n=len(stats), same=all(torch.equal(other[0], o) for o in other)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_unequal_shards_run_the_same_number_of_minibatches():
+    """shard_range gives the first W % G ranks one world more; every minibatch issues collectives, so all ranks must loop the
+    same number of times (the all-reduced minimum) instead of hanging on the first unmatched all_reduce."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run_unequal, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = ret.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok == dict(n=4, same=True), ok
+    assert all(p.exitcode == 0 for p in procs)
