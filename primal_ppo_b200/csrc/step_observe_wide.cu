@@ -23,10 +23,11 @@ namespace {
 using namespace ow;
 using namespace sww;
 
-constexpr int FW_WARPS = 8;
-
-template <int C_T, int F_T, bool VEC4>
-__global__ void __launch_bounds__(FW_WARPS * 32)
+// WARPS per CTA / MINB resident CTAs per SM the kernel is compiled for.  The step phase of a world is latency-bound
+// (~20 us: eight barrier-separated phases, global loads, thread-0 sections) and only hides under the stores of OTHER
+// worlds, so what matters is the number of worlds in flight per SM = resident CTAs; small CTAs give more of them.
+template <int C_T, int F_T, bool VEC4, int FW_WARPS, int MINB>
+__global__ void __launch_bounds__(FW_WARPS * 32, MINB)
 step_observe_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, const MapfStepOut out, float *__restrict__ obs,
                          float *__restrict__ vec, const ObsLayout L, const int shared_bytes, const int scratch_off,
                          const int per_warp, int *__restrict__ work_counter) {
@@ -105,14 +106,19 @@ struct WidePlan {
     bool ok;
 };
 
-WidePlan make_plan(const EnvView &v, int out_bf16) {
+WidePlan make_plan(const EnvView &v, int out_bf16, int FW_WARPS) {
     WidePlan p;
     p.ok = false;
     const int PB = v.C * v.F * v.F;
-    // chunk size: per-warp scratch (aw + wb) of at most ~12 KB, and at least one chunk per warp when N allows it
+    // chunk size: at least one chunk per warp when N allows it; per-warp scratch (aw + wb) small enough for six resident
+    // CTAs (~36 KB each) while the chunk keeps at least 8 agents (phase 1 runs one lane per agent), 12 KB at most
+    const size_t staged = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, 8).off_goal + (((size_t)v.N * 8 + 15) / 16) * 16;
+    size_t budget = staged < 36 * 1024 ? (36 * 1024 - staged) / FW_WARPS : 0;
+    if (budget > 12 * 1024) budget = 12 * 1024;
+    auto per_warp_bytes = [&](int ch) { return (size_t)ch * ((PB + 31) / 32 + 2) * 4 * 2; };
     int CH = 32;
-    while (CH > 2 && ((size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 12 * 1024 || (v.N + CH - 1) / CH < FW_WARPS)) CH >>= 1;
-    if ((size_t)CH * ((PB + 31) / 32 + 2) * 4 * 2 > 28 * 1024) return p;
+    while (CH > 2 && ((v.N + CH - 1) / CH < FW_WARPS || per_warp_bytes(CH) > 12 * 1024 || (CH > 8 && per_warp_bytes(CH) > budget))) CH >>= 1;
+    if (per_warp_bytes(CH) > 28 * 1024) return p;
     p.L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
     p.L.alias = 0;
     p.L.out_bf16 = out_bf16;
@@ -133,12 +139,23 @@ WidePlan make_plan(const EnvView &v, int out_bf16) {
 // Shapes served by the CTA-per-world fused kernel: anything the joint step supports (N <= 128) whose staging fits.
 bool step_observe_wide_fusable(const EnvView &v) {
     if (v.N > NMAX) return false;
-    return make_plan(v, 0).ok;
+    return make_plan(v, 0, 8).ok;
 }
 
 cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
                                      int *work_counter, cudaStream_t stream, int out_bf16) {
-    const WidePlan p = make_plan(v, out_bf16);
+    // variant: MAPF_DBG_FLAGS bits 24-25 (experiments): 0 = default, 1 = 8 warps x 3 CTAs, 2 = 4 warps x 6, 3 = 4 warps x 8
+    // Default: 4-warp CTAs when six of them fit an SM (measured on 80x80x128, ms per step for FOV 9 / 15 / 21 / 31:
+    // two launches 0.861 / 0.971 / 0.950 / 1.032; 8 warps x 3: 1.033 / 1.018 / 0.887 / 1.027; 4 warps x 6: 0.701 / 0.898 /
+    // 0.870 / 1.077 — at FOV 31 the per-warp observation scratch leaves three 4-warp CTAs, too few warps for the stores).
+    int variant = (v.dbg_flags >> 24) & 3;
+    if (variant == 0) {
+        const WidePlan p4 = make_plan(v, out_bf16, 4);
+        variant = (p4.ok && p4.smem <= 40 * 1024) ? 2 : 1;
+    }
+    const int warps = variant == 1 ? 8 : 4;
+    WidePlan p = make_plan(v, out_bf16, warps);
+    if (!p.ok && warps == 4) { variant = 1; p = make_plan(v, out_bf16, 8); }
     if (!p.ok) return cudaErrorNotSupported;
     const int PB = v.C * v.F * v.F;
     const size_t al = out_bf16 ? 8 : 4;
@@ -147,18 +164,26 @@ cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, co
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e;
-#define LAUNCH(...)                                                                                                \
+#define LAUNCH(WARPS_, MINB_, ...)                                                                                 \
     do {                                                                                                           \
-        e = cudaFuncSetAttribute(step_observe_wide_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);  \
+        auto kern = step_observe_wide_kernel<__VA_ARGS__, WARPS_, MINB_>;                                          \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                  \
         if (e != cudaSuccess) return e;                                                                            \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_observe_wide_kernel<__VA_ARGS__>, FW_WARPS * 32, p.smem);     \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_ * 32, p.smem);                         \
         if (per_sm < 1) per_sm = 1;                                                                                \
         const int blocks = v.W < sms * per_sm ? v.W : sms * per_sm;                                                \
-        step_observe_wide_kernel<__VA_ARGS__><<<blocks, FW_WARPS * 32, p.smem, stream>>>(v, actions, out, obs, vec, p.L, p.shared_bytes, \
-                                                                                          p.scratch_off, p.per_warp, work_counter); \
+        kern<<<blocks, WARPS_ * 32, p.smem, stream>>>(v, actions, out, obs, vec, p.L, p.shared_bytes, p.scratch_off, p.per_warp, \
+                                                      work_counter);                                               \
     } while (0)
-    if (v.C == 6 && v.F == 9) { if (vec4) LAUNCH(6, 9, true); else LAUNCH(6, 9, false); }
-    else { if (vec4) LAUNCH(0, 0, true); else LAUNCH(0, 0, false); }
+#define LAUNCH_V(...)                                                                                              \
+    do {                                                                                                           \
+        if (variant == 1) LAUNCH(8, 3, __VA_ARGS__);                                                               \
+        else if (variant == 2) LAUNCH(4, 6, __VA_ARGS__);                                                          \
+        else LAUNCH(4, 8, __VA_ARGS__);                                                                            \
+    } while (0)
+    if (v.C == 6 && v.F == 9) { if (vec4) LAUNCH_V(6, 9, true); else LAUNCH_V(6, 9, false); }
+    else { if (vec4) LAUNCH_V(0, 0, true); else LAUNCH_V(0, 0, false); }
+#undef LAUNCH_V
 #undef LAUNCH
     return cudaGetLastError();
 }
