@@ -396,6 +396,19 @@ def cpu_port_throughput(budget_s, worlds, threads, seed=7):
     return worlds * N_AGENTS * steps / dt, steps, dt
 
 
+def python_reference(budget_s):
+    """The UNMODIFIED Python reference env (baseline/_ref, installed by baseline/install_ref.py where /root/reference exists)
+    timed on this box's host cores, one process per core: BASELINE configs[2]'s shape and configs[0]."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import cpu_baseline
+        if not cpu_baseline.available():
+            return {"unavailable": "baseline/_ref not shipped (install: python baseline/install_ref.py in the authoring container)"}
+        return {"40x40x32": cpu_baseline.run(40, 32, (0.0, 0.3), budget_s), "10x10x8": cpu_baseline.run(10, 8, (0.2, 0.2), budget_s)}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path alone (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -429,11 +442,16 @@ def run_reference(args):
             "dtype": "u8/i16 state, f32 obs", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU path on a bounded sample of the same workload"},
             "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample,
-                             "note": "C restatement of mapf_gym.py (oracle/mapf_oracle.c); the Python reference itself "
-                                     "measured 1.4e3 agent-steps/s per core at this shape (SURVEY.md §6) and cannot travel "
-                                     "to the GPU box"},
+                             "note": "C/OpenMP restatement of mapf_gym.py (oracle/mapf_oracle.c), pinned bit-exact to the "
+                                     "reference; the unmodified Python reference on the same cores is under python_reference"},
             "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    # the Python reference itself on the same cores (its own implementation of the same path, ~1e3 agent-steps/s per core):
+    # reported beside the port, which is the arm the driver's ratio is computed against
+    line["python_reference"] = python_reference(args.python_ref_budget)
+    pr = line["python_reference"].get("40x40x32", {}) if isinstance(line["python_reference"], dict) else {}
+    if pr.get("agent_steps_per_s"):
+        line["cpu_baseline"]["port_vs_python_reference"] = value / pr["agent_steps_per_s"]
     print(json.dumps(line), flush=True)
 
 
@@ -450,6 +468,7 @@ def main():
     ap.add_argument("--ppo-worlds", type=int, default=1024, help="worlds per GPU of the PPO extra")
     ap.add_argument("--ppo-steps", type=int, default=256, help="rollout length T of the PPO extra")
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
+    ap.add_argument("--python-ref-budget", type=float, default=8.0, help="seconds per config of Python-reference timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -732,6 +751,8 @@ def main():
             cv, csteps, cdt = cpu_port_throughput(args.cpu_budget, cw, threads)
             cpu = {"value": cv, "unit": "agent-steps/s", "cores": threads, "kind": "port",
                    "sample": f"{cw} worlds 40x40x32 agents, {csteps} steps in {cdt:.1f} s, {threads} OpenMP threads (oracle/mapf_oracle.c)"}
+            if not args.no_extras and args.python_ref_budget > 0:
+                cpu["python_reference"] = python_reference(args.python_ref_budget)
         line = {"metric": "agent-steps/sec step+observe (40x40, 32 agents)", "value": value, "unit": "agent-steps/s",
                 "n_gpus": world_size, "steps": K, "warmup": Wu, "ms_per_step": total_ms_max / K, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16 state, f32 obs", "data": "synthetic",
