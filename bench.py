@@ -223,7 +223,7 @@ def bench_strong(sc, dev, rank, world_size, steps):
     ring = [torch.randint(0, 5, (Wl, N_AGENTS), generator=gen, device=dev, dtype=torch.int8) for _ in range(8)]
     ms = timed_env_loop(env, ring, obs, vec, steps, dev, world_size, warmup=5)
     # the same through the split-phase host call (pinned actions in, per-agent results out, read one step behind)
-    hr = env.make_host_ring(slots=2, action_slots=8)
+    hr = env.make_host_ring(slots=2, action_slots=8, compact=True)
     for k, r in enumerate(ring):
         hr["action_ring"][k].copy_(r)
     for i in range(3):
@@ -238,7 +238,7 @@ def bench_strong(sc, dev, rank, world_size, steps):
         env.step_observe_host_begin(hr["action_ring"][i % 8], hr["slots"][(i + 3) & 1], obs, vec)
         if i > 0:
             env.host_wait(1)
-            _ = float(hr["slots"][(i + 2) & 1]["reward"][0, 0])
+            _ = int(hr["slots"][(i + 2) & 1]["packed"][0, 0])
     env.host_wait(0)
     torch.cuda.synchronize(dev)
     e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world_size)
@@ -502,37 +502,51 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    ring_h = env.make_host_ring(slots=2, action_slots=8)            # ONE pinned slab: 2 result slots + the runner's action ring
+    # ONE pinned slab: 2 result slots + the runner's action ring.  Compact wire format: all per-agent results of a step in
+    # 2 bytes per agent (lossless; mapf_decode_results_host expands them) — 4.5 MB instead of 25 MB per step and GPU, which
+    # is what keeps eight GPUs of one box below the host's PCIe / memory ceiling (the full f32 slab is timed as an extra)
+    ring_h = env.make_host_ring(slots=2, action_slots=8, compact=True)
     for k, r in enumerate(ring):
         ring_h["action_ring"][k].copy_(r)
     host_ring = [ring_h["action_ring"][k] for k in range(8)]
 
-    def run_e2e(n_calls):
+    def run_e2e(n_calls, ring_h=ring_h, sync_ranks=True):
         """n_calls env steps through the split-phase host call, wall clock, after 3 untimed calls.  Every step: the joint
         action is read from pinned host memory (H2D inside the call), ONE fused launch, the step's per-agent results come
         back with one D2H copy and are READ ON THE HOST — one step behind the launch, which is how a rollout loop consumes
         them (runner.py:84-99 only appends them).  Returns (seconds, h2d bytes, d2h bytes per step)."""
+        acts_h = ring_h["action_ring"]
         for i in range(3):
-            env.step_observe_host_begin(host_ring[i % 8], ring_h["slots"][i & 1], obs, vec)
+            env.step_observe_host_begin(acts_h[i % 8], ring_h["slots"][i & 1], obs, vec)
         env.host_wait(0)
-        barrier()
+        if sync_ranks:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         stamps = []
         sink = 0.0
         for i in range(n_calls):
-            h2d_, d2h_ = env.step_observe_host_begin(host_ring[i % 8], ring_h["slots"][(i + 3) & 1], obs, vec)
+            h2d_, d2h_ = env.step_observe_host_begin(acts_h[i % 8], ring_h["slots"][(i + 3) & 1], obs, vec)
             if i > 0:
                 env.host_wait(1)                                         # step i-1 has landed while step i runs
-                sink += float(ring_h["slots"][(i + 2) & 1]["reward"][0, 0])
+                sink += read_reward(ring_h["slots"][(i + 2) & 1])
             stamps.append(time.perf_counter())
         env.host_wait(0)
-        sink += float(ring_h["slots"][(n_calls + 2) & 1]["reward"][0, 0])
+        sink += read_reward(ring_h["slots"][(n_calls + 2) & 1])
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if os.environ.get("BENCH_E2E_DEBUG"):
             d = [round((b - a) * 1e3, 3) for a, b in zip([t0] + stamps[:-1], stamps)]
             print("e2e per-call ms:", d, "mean", round(dt / n_calls * 1e3, 3), file=sys.stderr)
         return dt, h2d_, d2h_
+
+    def read_reward(slot):
+        """The host reads a result of the step: agent (0, 0)'s reward, decoded from the packed record in compact mode."""
+        if "packed" in slot:
+            p = int(slot["packed"][0, 0]) & 0xffff
+            return (-2.0, -2.0, -2.0, -0.35, -0.3)[min(p & 7, 4)] + (1.5 if p & 8 else 0.0)
+        return float(slot["reward"][0, 0])
 
     def run_e2e_sync(n_calls):
         """The synchronous form (mapf_step_observe_host: results on the host before the call returns)."""
@@ -629,6 +643,17 @@ def main():
 
     line_extra = {}
     if rank == 0 and not args.no_extras:
+        try:
+            full = env.make_host_ring(slots=2, action_slots=8, compact=False)
+            for k, r in enumerate(ring):
+                full["action_ring"][k].copy_(r)
+            fs, fh, fd = run_e2e(min(Ke, 20), full, sync_ranks=False)
+            line_extra["e2e_full_f32_slab"] = {"value": Wn * N * min(Ke, 20) / fs, "unit": "agent-steps/s (this rank)",
+                                               "d2h_bytes_per_step": fd,
+                                               "note": "the same split-phase call with the 12-byte-per-agent result slab"}
+            del full
+        except Exception as ex:
+            line_extra["e2e_full_f32_slab"] = {"error": str(ex)[:200]}
         try:
             line_extra["e2e_synchronous_call"] = {"value": Wn * N * 10 / run_e2e_sync(10), "unit": "agent-steps/s (1 GPU)",
                                                   "note": "mapf_step_observe_host: results on the host before the call returns"}
@@ -763,10 +788,11 @@ def main():
                            "worlds_with_error_flags": err_frac},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": Ke, "note": "mapf_step_observe_host_begin/_wait (split-phase): every step the joint action comes "
-                                             "from pinned host memory (H2D), ONE fused launch, and ALL per-agent results (status, "
-                                             "reward, cost, goals reached, violations, shadow goals, executed actions) return in one "
-                                             "D2H copy of a contiguous slab and are read on the host one step behind the launch; "
+                        "steps": Ke, "note": "mapf_step_observe_host_begin/_wait (split-phase, compact wire format): every step the joint "
+                                             "action comes from pinned host memory (H2D), ONE fused launch, and ALL per-agent results "
+                                             "(status, reward, cost, goals reached, violations, executed actions: 16 bits per agent, "
+                                             "lossless, + shadow goals) return in one D2H copy and are read on the host one step behind "
+                                             "the launch; "
                                              "observations and trainValid stay in HBM as the policy's / learner's input tensors"},
                 "gpu_launches": K,
                 "roofline": {"bound": "hbm", "kernel": "step_observe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -105,10 +105,24 @@ typedef struct MapfStepOut {
     uint8_t *violated;     /* [W,N]   jointStep()[1] */
     int32_t *shadow_goals; /* [W]     calculateActionReward()[1] */
     int8_t *fixed_actions; /* [W,N]   the actions actually executed (after fixActions, mapf_gym.py:552-612) */
+    uint16_t *packed;      /* [W,N]   every per-agent result of the step in 16 bits (lossless; MAPF_PACKED_* below): what the
+                              split-phase host call ships over PCIe in compact mode.  Written by mapf_step / mapf_step_observe. */
     uint8_t *good_actions; /* [W,N]   MapfGym.allGoodActions (mapf_gym.py:404-430, refreshed at :169/:635) as 5-bit masks, bit a =
                               action a is unconditionally good in the CURRENT state; written by mapf_evaluate only (the
                               masks do not depend on the actions passed) */
 } MapfStepOut;
+
+/* MapfStepOut.packed: bits 0-2 status code (0: -1 static, 1: -2 human, 2: -3 agent, 3: -4 repeat, 4: +1 ok), bit 3
+ * goal reached, bit 4 constraint violated, bits 5-7 the executed action (after fixActions), bits 8-12 min(d2, 25) with d2 the
+ * squared distance between human.getNextPos() and the agent's (unfixed) target cell.  The f32 outputs are functions of
+ * these fields:  reward = {-2, -2, -2, -0.35, -0.3}[status code] (+ 1.5 when goal reached, runner.py:89-91);
+ * cost = d2 < 25 ? (float)((5.0 - sqrt((double)d2)) / 5.0) : 0   (mapf_gym.py:513-533).  mapf_decode_results_host expands
+ * a packed array into the reference's arrays on the host, bit for bit. */
+#define MAPF_PACKED_STATUS(p) ((int)((p) & 7u))
+#define MAPF_PACKED_GOAL(p) ((int)(((p) >> 3) & 1u))
+#define MAPF_PACKED_VIOLATED(p) ((int)(((p) >> 4) & 1u))
+#define MAPF_PACKED_ACTION(p) ((int)(((p) >> 5) & 7u))
+#define MAPF_PACKED_D2(p) ((int)(((p) >> 8) & 31u))
 
 int mapf_abi_version(void);
 const char *mapf_last_error(void);
@@ -230,7 +244,7 @@ int mapf_generate_scenario(const MapfGenConfig *cfg, uint8_t *obst /*[W,H,Wd]*/,
  * slower than slices of a single slab). */
 typedef struct MapfStepOutHost {
     int8_t *status; float *reward; float *cost; float *train_valid; uint8_t *goals_reached; uint8_t *violated;
-    int32_t *shadow_goals; int8_t *fixed_actions; uint8_t *good_actions /* ignored */;
+    int32_t *shadow_goals; int8_t *fixed_actions; uint16_t *packed /* ignored */; uint8_t *good_actions /* ignored */;
 } MapfStepOutHost;
 
 /* SYNCHRONOUS form.  actions_host -> device, mapf_step, mapf_observe into obs_dev/vec_dev (device; the policy's input
@@ -246,27 +260,37 @@ int mapf_step_observe_host(MapfEnv *env, const int8_t *actions_host, const MapfS
  * host while step t+1 computes.
  *
  * All per-agent results of one step live in ONE contiguous "result slot" whose layout mapf_host_layout reports (same
- * layout on the device and on the host; every field 256-byte aligned):
- *   reward f32[W,N] | cost f32[W,N] | shadow_goals i32[W] | status i8[W,N] | goals_reached u8[W,N] | violated u8[W,N] |
- *   fixed_actions i8[W,N] | (train_valid f32[W,N,5] when with_train_valid)
+ * layout on the device and on the host; every field 256-byte aligned).  Two wire formats, chosen by `flags`:
+ *   full (default):        reward f32[W,N] | cost f32[W,N] | shadow_goals i32[W] | status i8[W,N] | goals_reached u8[W,N] |
+ *                          violated u8[W,N] | fixed_actions i8[W,N]                       (12 B per agent)
+ *   MAPF_HOST_COMPACT:     packed u16[W,N] (MapfStepOut.packed) | shadow_goals i32[W]     (2 B per agent, lossless;
+ *                          mapf_decode_results_host expands it).  Eight GPUs of one box share the host's PCIe / memory
+ *                          path: at 65 536 x 32 agents the full slab is 25 MB per step and GPU, the compact one 4.5 MB.
+ *   | MAPF_HOST_TRAIN_VALID: train_valid f32[W,N,5] appended (needs train_valid_dev; the caller's tensor is the copy
+ *                          source, so the next begin waits for this step's copy).
  * mapf_step_observe_host_begin: actions_host -> device (own copy stream, double-buffered), ONE fused step+observe launch
  * on `stream` writing obs_dev / vec_dev (and train_valid_dev if given) and the env's device slot, then ONE device-to-host
  * copy of the slot into result_slot_host on the copy stream.  Returns without any host synchronisation: work queued on
  * `stream` afterwards (the policy forward) sees obs_dev / vec_dev of this step.  The env keeps two device slots, so two
  * begins may be in flight; result_slot_host must stay untouched until the matching wait.
  * mapf_step_observe_host_wait(env, age): block the host until the results of the most recent begin (age 0) or of the one
- * before it (age 1) have landed in their result_slot_host.
- * with_train_valid != 0 needs train_valid_dev and makes the next begin wait for this step's copy (the caller's
- * trainValid tensor is the copy source). */
+ * before it (age 1) have landed in their result_slot_host. */
+#define MAPF_HOST_TRAIN_VALID 1
+#define MAPF_HOST_COMPACT 2
 typedef struct MapfHostLayout {
-    int64_t slot_bytes; /* bytes of one result slot (with_train_valid as passed to mapf_host_layout) */
+    int64_t slot_bytes; /* bytes of one result slot for the flags passed to mapf_host_layout */
     int64_t off_reward, off_cost, off_shadow_goals, off_status, off_goals_reached, off_violated, off_fixed_actions,
-        off_train_valid; /* -1 when absent */
+        off_train_valid, off_packed; /* -1 when absent */
 } MapfHostLayout;
-int mapf_host_layout(MapfEnv *env, int with_train_valid, MapfHostLayout *out);
-int mapf_step_observe_host_begin(MapfEnv *env, const int8_t *actions_host, void *result_slot_host, int with_train_valid,
+int mapf_host_layout(MapfEnv *env, int flags, MapfHostLayout *out);
+int mapf_step_observe_host_begin(MapfEnv *env, const int8_t *actions_host, void *result_slot_host, int flags,
                                  float *obs_dev, float *vec_dev, float *train_valid_dev, void *stream);
 int mapf_step_observe_host_wait(MapfEnv *env, int age);
+
+/* HOST function (no GPU work): expand n packed results (MapfStepOut.packed / a compact slot's `packed` field) into the
+ * reference's per-agent arrays; any pointer of `out` may be NULL; out->train_valid / shadow_goals / good_actions are not
+ * touched.  Bit-identical to the arrays the full format carries. */
+int mapf_decode_results_host(const uint16_t *packed, int64_t n, const MapfStepOutHost *out);
 
 /* ---- integrity helper ------------------------------------------------------------------------------------------------- */
 

@@ -15,7 +15,7 @@ EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy"
             "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe",
             "mapf_sample_actions", "mapf_generate_scenario",
             "mapf_observe_bf16", "mapf_step_observe_bf16", "mapf_state_bytes", "mapf_save_state", "mapf_load_state",
-            "mapf_get_human", "mapf_host_layout", "mapf_step_observe_host_begin", "mapf_step_observe_host_wait", "mapf_checksum_rows"]
+            "mapf_get_human", "mapf_host_layout", "mapf_step_observe_host_begin", "mapf_step_observe_host_wait", "mapf_decode_results_host", "mapf_checksum_rows"]
 ABI_VERSION = 2
 
 ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE, ERR_NO_FREE_CELL = 1, 2, 4, 8, 64
@@ -44,7 +44,7 @@ class MapfScenario(C.Structure):
 class MapfStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals",
-                 "fixed_actions", "good_actions")]
+                 "fixed_actions", "packed", "good_actions")]
 
 
 MapfStepOutHost = MapfStepOut   # same layout, host pointers
@@ -53,7 +53,10 @@ MapfStepOutHost = MapfStepOut   # same layout, host pointers
 class MapfHostLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("slot_bytes", "off_reward", "off_cost", "off_shadow_goals", "off_status", "off_goals_reached",
-                 "off_violated", "off_fixed_actions", "off_train_valid")]
+                 "off_violated", "off_fixed_actions", "off_train_valid", "off_packed")]
+
+
+HOST_TRAIN_VALID, HOST_COMPACT = 1, 2
 
 
 class MapfError(RuntimeError):
@@ -101,6 +104,7 @@ def load_library():
     lib.mapf_step_observe_host_begin.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.mapf_step_observe_host_wait.argtypes = [vp, C.c_int]
     lib.mapf_checksum_rows.argtypes = [vp, i64, i64, vp, vp]
+    lib.mapf_decode_results_host.argtypes = [vp, i64, C.POINTER(MapfStepOutHost)]
     for n in EXPORTED:
         if n not in ("mapf_last_error",):
             getattr(lib, n).restype = C.c_int

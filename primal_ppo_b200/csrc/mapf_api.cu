@@ -1,4 +1,5 @@
 // mapf_api.cu — the C ABI declared in include/mapf_b200.h (handle, reset, argument checking, host-buffer calls).
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -24,7 +25,8 @@ struct MapfEnv {
     // two result slots (layout: MapfHostLayout without train_valid) and two action buffers, used alternately
     unsigned char *d_slot[2];
     int8_t *d_actions[2];
-    MapfHostLayout lay;                      // layout of a slot (no train_valid)
+    MapfHostLayout lay;                      // layout of a full slot (no train_valid)
+    MapfHostLayout lay_c;                    // layout of a compact slot (packed + shadow goals), carved from the same memory
     cudaStream_t copy_stream, h2d_stream;
     cudaEvent_t ev_step[2], ev_copied[2], ev_h2d[2];
     bool tv_copy_pending[2];                 // that begin also copied the caller's trainValid tensor
@@ -175,7 +177,14 @@ int mapf_create(const MapfConfig *cfg, MapfEnv **out) {
         L.off_violated = (int64_t)o; o += up(WN);
         L.off_fixed_actions = (int64_t)o; o += up(WN);
         L.off_train_valid = -1;
+        L.off_packed = -1;
         L.slot_bytes = (int64_t)o;
+        MapfHostLayout &Lc = e->lay_c;
+        Lc.off_reward = Lc.off_cost = Lc.off_status = Lc.off_goals_reached = Lc.off_violated = Lc.off_fixed_actions = -1;
+        Lc.off_train_valid = -1;
+        Lc.off_packed = 0;
+        Lc.off_shadow_goals = (int64_t)up(WN * 2);
+        Lc.slot_bytes = Lc.off_shadow_goals + (int64_t)up(W * 4);
     }
     for (int k = 0; k < 2; ++k) {
         alloc((void **)&e->d_slot[k], (size_t)e->lay.slot_bytes);
@@ -502,40 +511,71 @@ int queue_actions(MapfEnv *e, int k, const int8_t *actions_host, cudaStream_t s)
 
 }  // namespace
 
-int mapf_host_layout(MapfEnv *e, int with_train_valid, MapfHostLayout *out) {
+int mapf_host_layout(MapfEnv *e, int flags, MapfHostLayout *out) {
     if (!e || !out) return fail(MAPF_E_NULL, "mapf_host_layout: null argument");
-    *out = e->lay;
-    if (with_train_valid) {
+    *out = (flags & MAPF_HOST_COMPACT) ? e->lay_c : e->lay;
+    if (flags & MAPF_HOST_TRAIN_VALID) {
         out->off_train_valid = out->slot_bytes;
         out->slot_bytes += (int64_t)((((size_t)e->v.W * e->v.N * NA * 4) + 255) & ~(size_t)255);
     }
     return MAPF_OK;
 }
 
-int mapf_step_observe_host_begin(MapfEnv *e, const int8_t *actions_host, void *result_slot_host, int with_train_valid,
+int mapf_step_observe_host_begin(MapfEnv *e, const int8_t *actions_host, void *result_slot_host, int flags,
                                  float *obs_dev, float *vec_dev, float *train_valid_dev, void *stream) {
     NEED_ENV("mapf_step_observe_host_begin");
     if (int rc = check_vec(vec_dev, "mapf_step_observe_host_begin")) return rc;
     if (!actions_host || !result_slot_host || !obs_dev || !vec_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host_begin: null argument");
-    if (with_train_valid && !train_valid_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host_begin: with_train_valid needs train_valid_dev");
+    const bool with_tv = flags & MAPF_HOST_TRAIN_VALID, compact = flags & MAPF_HOST_COMPACT;
+    if (with_tv && !train_valid_dev) return fail(MAPF_E_NULL, "mapf_step_observe_host_begin: MAPF_HOST_TRAIN_VALID needs train_valid_dev");
     if (int rc = check_step_n(e, "mapf_step_observe_host_begin")) return rc;
     const EnvView &v = e->v;
     cudaStream_t s = (cudaStream_t)stream, cs = e->copy_stream;
     const int k = e->next_slot;
     if (int rc = queue_actions(e, k, actions_host, s)) return rc;
-    MapfStepOut o = slot_ptrs(e, k);
+    MapfStepOut o;
+    size_t slot_bytes;
+    if (compact) {
+        memset(&o, 0, sizeof(o));
+        o.packed = reinterpret_cast<uint16_t *>(e->d_slot[k] + e->lay_c.off_packed);
+        o.shadow_goals = reinterpret_cast<int32_t *>(e->d_slot[k] + e->lay_c.off_shadow_goals);
+        slot_bytes = (size_t)e->lay_c.slot_bytes;
+    } else {
+        o = slot_ptrs(e, k);
+        slot_bytes = (size_t)e->lay.slot_bytes;
+    }
     o.train_valid = train_valid_dev;
     CU(do_step_observe(e, e->d_actions[k], o, obs_dev, vec_dev, s, 0));
     CU(cudaEventRecord(e->ev_step[k], s));
     CU(cudaStreamWaitEvent(cs, e->ev_step[k], 0));
-    CU(cudaMemcpyAsync(result_slot_host, e->d_slot[k], (size_t)e->lay.slot_bytes, cudaMemcpyDeviceToHost, cs));   // ONE copy
-    if (with_train_valid)
-        CU(cudaMemcpyAsync(static_cast<char *>(result_slot_host) + e->lay.slot_bytes, train_valid_dev,
+    CU(cudaMemcpyAsync(result_slot_host, e->d_slot[k], slot_bytes, cudaMemcpyDeviceToHost, cs));   // ONE copy
+    if (with_tv)
+        CU(cudaMemcpyAsync(static_cast<char *>(result_slot_host) + slot_bytes, train_valid_dev,
                            (size_t)v.W * v.N * NA * 4, cudaMemcpyDeviceToHost, cs));
     CU(cudaEventRecord(e->ev_copied[k], cs));
-    e->tv_copy_pending[k] = with_train_valid != 0;
+    e->tv_copy_pending[k] = with_tv;
     e->next_slot = k ^ 1;
     if (e->begun < 2) e->begun++;
+    return MAPF_OK;
+}
+
+int mapf_decode_results_host(const uint16_t *packed, int64_t n, const MapfStepOutHost *out) {
+    if (!packed || !out) return fail(MAPF_E_NULL, "mapf_decode_results_host: null argument");
+    if (n < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_decode_results_host: n < 0");
+    static const int8_t status_of[8] = {-1, -2, -3, -4, 1, 1, 1, 1};
+    static const float base_reward[8] = {-2.0f, -2.0f, -2.0f, -0.35f, -0.3f, -0.3f, -0.3f, -0.3f};   // alg_parameters.py:36-43
+    float reward_lut[16], cost_lut[32];
+    for (int k = 0; k < 16; ++k) reward_lut[k] = (k & 8) ? base_reward[k & 7] + 1.5f : base_reward[k & 7];   // runner.py:89-91
+    for (int d2 = 0; d2 < 32; ++d2) cost_lut[d2] = d2 < 25 ? (float)((5.0 - sqrt((double)d2)) / 5.0) : 0.0f;  // mapf_gym.py:513-533
+    for (int64_t i = 0; i < n; ++i) {
+        const unsigned p = packed[i];
+        if (out->status) out->status[i] = status_of[p & 7u];
+        if (out->reward) out->reward[i] = reward_lut[p & 15u];
+        if (out->cost) out->cost[i] = cost_lut[(p >> 8) & 31u];
+        if (out->goals_reached) out->goals_reached[i] = (uint8_t)((p >> 3) & 1u);
+        if (out->violated) out->violated[i] = (uint8_t)((p >> 4) & 1u);
+        if (out->fixed_actions) out->fixed_actions[i] = (int8_t)((p >> 5) & 7u);
+    }
     return MAPF_OK;
 }
 

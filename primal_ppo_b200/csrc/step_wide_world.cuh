@@ -310,6 +310,14 @@ __device__ __forceinline__ void step_wide_world(const EnvView &v, const int8_t *
                 const float reward = st == ST_REPEAT ? -0.35f : st == ST_OK ? -0.3f : -2.0f;
                 out.reward[base + i] = arrived ? __fadd_rn(reward, 1.5f) : reward;           // runner.py:89-91
             }
+            if (MODE == MODE_FUSED && out.packed) {                              // MAPF_PACKED_* (include/mapf_b200.h)
+                const int st = s.st[i], a = s.act[i];
+                const int tr = (int16_t)(pw & 0xffff) + dr_of(a), tc = (int16_t)(pw >> 16) + dc_of(a);
+                const int d2 = (nr - tr) * (nr - tr) + (nc - tc) * (nc - tc);
+                const uint32_t sc = st == ST_STATIC ? 0u : st == ST_HUMAN ? 1u : st == ST_AGENT ? 2u : st == ST_REPEAT ? 3u : 4u;
+                out.packed[base + i] = (uint16_t)(sc | ((uint32_t)arrived << 3) | ((uint32_t)viol << 4) | ((uint32_t)f << 5) |
+                                                  ((uint32_t)min(d2, 25) << 8));
+            }
             n_arr += arrived; n_viol += viol;
         }
         if (n_arr) atomicAdd(&s.cnt[K_ARR], n_arr);

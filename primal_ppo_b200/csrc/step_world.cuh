@@ -174,11 +174,11 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
     float reward = st == ST_REPEAT ? -0.35f : st == ST_OK ? -0.3f : -2.0f;       // alg_parameters.py:36-43
     const bool sg = active && st == ST_OK && tgt_r == goal_r && tgt_c == goal_c;       // shadowGoal :501-504
     const uint32_t sgm = __ballot_sync(FULL, sg);
+    const int d2 = (nr - tgt_r) * (nr - tgt_r) + (nc - tgt_c) * (nc - tgt_c);    // |human.getNextPos() - T(a)|^2 (:519)
     if (MODE != MODE_JOINT) {
         if (active) {
             if (out.status) out.status[idx] = (int8_t)st;
             if (out.cost) {
-                const int d2 = (nr - tgt_r) * (nr - tgt_r) + (nc - tgt_c) * (nc - tgt_c);
                 // max(PENALTY_RADIUS - ||H' - T||, 0) / PENALTY_RADIUS in f64, then cast (:513-533)
                 out.cost[idx] = d2 < 25 ? (float)((5.0 - sqrt((double)d2)) / 5.0) : 0.0f;
             }
@@ -379,6 +379,11 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
         if (out.violated) out.violated[idx] = viol;
         if (out.fixed_actions) out.fixed_actions[idx] = (int8_t)f;
         if (MODE == MODE_FUSED && out.reward) out.reward[idx] = arrived ? __fadd_rn(reward, 1.5f) : reward;  // runner.py:89-91
+        if (MODE == MODE_FUSED && out.packed) {                                  // MAPF_PACKED_* (include/mapf_b200.h)
+            const uint32_t sc = st == ST_STATIC ? 0u : st == ST_HUMAN ? 1u : st == ST_AGENT ? 2u : st == ST_REPEAT ? 3u : 4u;
+            out.packed[idx] = (uint16_t)(sc | ((uint32_t)arrived << 3) | ((uint32_t)viol << 4) | ((uint32_t)f << 5) |
+                                         ((uint32_t)min(d2, 25) << 8));
+        }
     }
     const uint32_t vm_ = __ballot_sync(FULL, viol);
     const uint32_t c1 = __ballot_sync(FULL, active && st == ST_STATIC), c2b = __ballot_sync(FULL, active && st == ST_HUMAN),

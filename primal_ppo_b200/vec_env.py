@@ -51,6 +51,7 @@ class StepOut:
     shadow_goals: torch.Tensor   # int32 [W]
     fixed_actions: torch.Tensor  # int8  [W,N]
     good_actions: Optional[torch.Tensor] = None   # uint8 [W,N] allGoodActions masks (mapf_evaluate only)
+    packed: Optional[torch.Tensor] = None         # int16 [W,N] all per-agent results in 16 bits (MAPF_PACKED_*; step / step_observe)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -168,7 +169,8 @@ class BatchedMapfGym:
                                  train_valid=o.train_valid.data_ptr(), goals_reached=o.goals_reached.data_ptr(),
                                  violated=o.violated.data_ptr(), shadow_goals=o.shadow_goals.data_ptr(),
                                  fixed_actions=o.fixed_actions.data_ptr(),
-                                 good_actions=None if o.good_actions is None else o.good_actions.data_ptr())
+                                 good_actions=None if o.good_actions is None else o.good_actions.data_ptr(),
+                                 packed=None if o.packed is None else o.packed.data_ptr())
 
     def _ret(self, t):
         return t.clone() if self._fresh else t
@@ -406,20 +408,23 @@ class BatchedMapfGym:
 
 
     # ---- split-phase host call: step t's results travel to the host while step t+1 computes -------------------------
-    def host_layout(self, with_train_valid: bool = False) -> "_cabi.MapfHostLayout":
-        key = bool(with_train_valid)
-        if key not in self._host_layouts:
+    def host_layout(self, with_train_valid: bool = False, compact: bool = False) -> "_cabi.MapfHostLayout":
+        flags = (_cabi.HOST_TRAIN_VALID if with_train_valid else 0) | (_cabi.HOST_COMPACT if compact else 0)
+        if flags not in self._host_layouts:
             L = _cabi.MapfHostLayout()
-            _cabi.check(self._lib.mapf_host_layout(self._h, int(key), C.byref(L)), "mapf_host_layout")
-            self._host_layouts[key] = L
-        return self._host_layouts[key]
+            _cabi.check(self._lib.mapf_host_layout(self._h, flags, C.byref(L)), "mapf_host_layout")
+            self._host_layouts[flags] = L
+        return self._host_layouts[flags]
 
-    def make_host_ring(self, slots: int = 2, action_slots: int = 2, with_train_valid: bool = False, numa_bind: bool = True):
+    def make_host_ring(self, slots: int = 2, action_slots: int = 2, with_train_valid: bool = False, compact: bool = False,
+                       numa_bind: bool = True):
         """ONE pinned slab holding `slots` result slots (the layout ``mapf_host_layout`` reports: every per-agent result of
         a step is contiguous, so a step's results come back with one copy) and an int8 [action_slots, W, N] action ring.
-        Returns ``{"slots": [dict of views per slot], "action_ring": ..., "_slab": ...}``.  numa_bind: allocate while the
-        calling thread is bound to the CPUs next to this GPU (first-touch places the pages on the GPU's NUMA node)."""
-        L = self.host_layout(with_train_valid)
+        compact=True: the 2-byte-per-agent wire format (``packed`` u16 [W,N] + ``shadow_goals``; ``decode_slot`` expands it
+        on the host, bit for bit) instead of the 12-byte-per-agent f32 slab — what keeps eight GPUs of one box off the
+        host's PCIe / memory ceiling.  Returns ``{"slots": [dict of views per slot], "action_ring": ..., ...}``.
+        numa_bind: allocate while the calling thread is bound to the CPUs next to this GPU (first touch places the pages)."""
+        L = self.host_layout(with_train_valid, compact)
         W, N = self.W, self.N
         sb = int(L.slot_bytes)
         act_bytes = (max(1, action_slots) * W * N + 255) // 256 * 256
@@ -436,38 +441,62 @@ class BatchedMapfGym:
 
             def f(off, n, dt, shape):
                 return b[off:off + n].view(dt).view(shape)
-            d = dict(reward=f(L.off_reward, W * N * 4, torch.float32, (W, N)), cost=f(L.off_cost, W * N * 4, torch.float32, (W, N)),
-                     shadow_goals=f(L.off_shadow_goals, W * 4, torch.int32, (W,)), status=f(L.off_status, W * N, torch.int8, (W, N)),
-                     goals_reached=f(L.off_goals_reached, W * N, torch.uint8, (W, N)),
-                     violated=f(L.off_violated, W * N, torch.uint8, (W, N)),
-                     fixed_actions=f(L.off_fixed_actions, W * N, torch.int8, (W, N)), _raw=b)
+            d = dict(shadow_goals=f(L.off_shadow_goals, W * 4, torch.int32, (W,)), _raw=b)
+            if compact:
+                d["packed"] = f(L.off_packed, W * N * 2, torch.int16, (W, N))
+            else:
+                d.update(reward=f(L.off_reward, W * N * 4, torch.float32, (W, N)), cost=f(L.off_cost, W * N * 4, torch.float32, (W, N)),
+                         status=f(L.off_status, W * N, torch.int8, (W, N)),
+                         goals_reached=f(L.off_goals_reached, W * N, torch.uint8, (W, N)),
+                         violated=f(L.off_violated, W * N, torch.uint8, (W, N)),
+                         fixed_actions=f(L.off_fixed_actions, W * N, torch.int8, (W, N)))
             if with_train_valid:
                 d["train_valid"] = f(L.off_train_valid, W * N * 20, torch.float32, (W, N, 5))
             views.append(d)
         ring = slab[slots * sb:slots * sb + max(1, action_slots) * W * N].view(torch.int8).view(max(1, action_slots), W, N)
         return {"slots": views, "action_ring": ring, "_slab": slab, "with_train_valid": bool(with_train_valid),
-                "slot_bytes": sb}
+                "compact": bool(compact), "slot_bytes": sb,
+                "flags": (_cabi.HOST_TRAIN_VALID if with_train_valid else 0) | (_cabi.HOST_COMPACT if compact else 0)}
 
     def step_observe_host_begin(self, actions: torch.Tensor, slot: dict, obs_dev: torch.Tensor, vec_dev: torch.Tensor,
                                 train_valid_dev: Optional[torch.Tensor] = None, with_train_valid: bool = False):
         """Queue one env step for a HOST runner and return immediately: `actions` (int8 [W,N] host tensor, ideally a slice of
         the ring's pinned slab) -> device, ONE fused step+observe launch into obs_dev / vec_dev, all per-agent results ->
-        `slot` (one of ``make_host_ring()["slots"]``) with ONE device-to-host copy.  ``host_wait(age)`` makes a slot
-        readable.  Returns (h2d_bytes, d2h_bytes)."""
+        `slot` (one of ``make_host_ring()["slots"]``; its format — full or compact — is the ring's) with ONE device-to-host
+        copy.  ``host_wait(age)`` makes a slot readable.  Returns (h2d_bytes, d2h_bytes)."""
         assert not actions.is_cuda and actions.dtype == torch.int8 and actions.is_contiguous() and actions.numel() == self.W * self.N
+        compact = "packed" in slot
+        flags = (_cabi.HOST_TRAIN_VALID if with_train_valid else 0) | (_cabi.HOST_COMPACT if compact else 0)
         tvd = train_valid_dev
         if with_train_valid and tvd is None:
             tvd = self._out.train_valid
-        _cabi.check(self._lib.mapf_step_observe_host_begin(self._h, _ptr(actions), C.c_void_p(slot["_raw"].data_ptr()),
-                                                           int(bool(with_train_valid)), _ptr(obs_dev), _ptr(vec_dev),
-                                                           _ptr(tvd), self._stream()), "mapf_step_observe_host_begin")
+        _cabi.check(self._lib.mapf_step_observe_host_begin(self._h, _ptr(actions), C.c_void_p(slot["_raw"].data_ptr()), flags,
+                                                           _ptr(obs_dev), _ptr(vec_dev), _ptr(tvd), self._stream()),
+                    "mapf_step_observe_host_begin")
         self._eval_key = None
-        return actions.numel(), int(self.host_layout(with_train_valid).slot_bytes)
+        return actions.numel(), int(self.host_layout(with_train_valid, compact).slot_bytes)
 
     def host_wait(self, age: int = 0):
         """Block until the results of the most recent ``step_observe_host_begin`` (age 0) or the one before (age 1) are in
         their host slot."""
         _cabi.check(self._lib.mapf_step_observe_host_wait(self._h, int(age)), "mapf_step_observe_host_wait")
+
+
+def decode_results(packed: torch.Tensor, out: Optional[dict] = None) -> dict:
+    """``mapf_decode_results_host``: expand a HOST int16 / uint16 tensor of packed per-agent results (a compact slot's
+    ``packed``) into the reference's arrays — status i8, reward f32, cost f32, goals_reached u8, violated u8,
+    fixed_actions i8 — bit-identical to what the full format carries.  `out` (same keys) is reused when given."""
+    lib = _cabi.load_library()
+    assert not packed.is_cuda and packed.is_contiguous() and packed.element_size() == 2
+    shp = tuple(packed.shape)
+    if out is None:
+        out = dict(status=torch.empty(shp, dtype=torch.int8), reward=torch.empty(shp, dtype=torch.float32),
+                   cost=torch.empty(shp, dtype=torch.float32), goals_reached=torch.empty(shp, dtype=torch.uint8),
+                   violated=torch.empty(shp, dtype=torch.uint8), fixed_actions=torch.empty(shp, dtype=torch.int8))
+    so = _cabi.MapfStepOutHost(**{k: out[k].data_ptr() for k in ("status", "reward", "cost", "goals_reached", "violated",
+                                                                  "fixed_actions") if k in out})
+    _cabi.check(lib.mapf_decode_results_host(C.c_void_p(packed.data_ptr()), packed.numel(), C.byref(so)), "mapf_decode_results_host")
+    return out
 
 
 def _bind_near_gpu(device):

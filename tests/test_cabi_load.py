@@ -44,8 +44,8 @@ def test_config_struct_layout_matches_header():
     assert _cabi.MapfConfig.seed.offset == 48
     assert _cabi.MapfConfig.goal_sampling.offset == 64
     assert ctypes.sizeof(_cabi.MapfScenario) == 9 * 8
-    assert ctypes.sizeof(_cabi.MapfStepOut) == 9 * 8
-    assert ctypes.sizeof(_cabi.MapfHostLayout) == 9 * 8
+    assert ctypes.sizeof(_cabi.MapfStepOut) == 10 * 8
+    assert ctypes.sizeof(_cabi.MapfHostLayout) == 10 * 8
 
 
 def test_null_arguments_are_rejected_without_gpu(lib_path):

@@ -139,3 +139,34 @@ def test_goal_sampling_distribution_matches_live_reference():
     chi2 = float((((ref[m] - ours[m]) ** 2) / (ref[m] + ours[m])).sum())
     n = int(m.sum())
     assert chi2 < n + 6 * np.sqrt(2 * n), (chi2, n)
+
+
+def test_packed_results_decoder_matches_oracle_outputs():
+    """mapf_decode_results_host (a HOST function of the C-ABI library; no GPU involved) on words packed from the oracle's
+    outputs per the MAPF_PACKED_* definition: every decoded array equals the oracle's, bit for bit — in particular
+    reward = base(status) (+1.5 on arrival) and cost = f(d2) are reproduced from the 16-bit record."""
+    import torch
+    from primal_ppo_b200 import decode_results, random_actions, random_scenario
+    sc = random_scenario(64, 12, 12, 8, density=(0.1, 0.3), queue_len=3, seed=4)
+    orc = OracleMapfGym(sc, threads=2, use_tape=False)
+    acts = random_actions(24, 64, 8, seed=1)
+    DR, DC = np.array([0, 0, 1, 0, -1]), np.array([0, 1, 0, -1, 0])
+    code = {-1: 0, -2: 1, -3: 2, -4: 3, 1: 4}
+    for t in range(24):
+        pos = orc.state()["pos"].astype(np.int64)
+        tick = t % sc.hlen
+        nxt = sc.htrace[np.arange(64), tick, 2:].astype(np.int64)
+        out = orc.step(acts[t])
+        a = acts[t].astype(np.int64)
+        tr, tc = pos[..., 0] + DR[a], pos[..., 1] + DC[a]
+        d2 = np.minimum((nxt[:, None, 0] - tr) ** 2 + (nxt[:, None, 1] - tc) ** 2, 25)
+        sc_ = np.vectorize(code.get)(out["status"].astype(np.int64))
+        packed = (sc_ | (out["goals_reached"].astype(np.int64) << 3) | (out["violated"].astype(np.int64) << 4) |
+                  (out["fixed"].astype(np.int64) << 5) | (d2 << 8)).astype(np.uint16)
+        dec = decode_results(torch.from_numpy(packed.view(np.int16)))
+        np.testing.assert_array_equal(dec["status"].numpy(), out["status"])
+        np.testing.assert_array_equal(dec["reward"].numpy().view(np.uint32), out["reward"].view(np.uint32))
+        np.testing.assert_array_equal(dec["cost"].numpy().view(np.uint32), out["cost"].view(np.uint32))
+        np.testing.assert_array_equal(dec["goals_reached"].numpy(), out["goals_reached"])
+        np.testing.assert_array_equal(dec["violated"].numpy(), out["violated"])
+        np.testing.assert_array_equal(dec["fixed_actions"].numpy(), out["fixed"])

@@ -155,6 +155,26 @@ def test_gpu_split_phase_host_call_equals_device_call(shape):
             assert torch.equal(obs_t[t & 1], want[t]["obs"]) and torch.equal(vec_t[t & 1], want[t]["vec"]), t
         env.host_wait(0)
         check(T - 1)
+    # compact wire format (2 bytes per agent): decoded on the host it equals the full slab bit for bit
+    from primal_ppo_b200 import decode_results
+    env.reset()
+    ring = env.make_host_ring(slots=2, action_slots=2, compact=True)
+    assert ring["slot_bytes"] < 3 * W * N + 4 * W + 1024
+    dec = None
+    for t in range(T):
+        ring["action_ring"][t & 1].copy_(torch.from_numpy(acts[t]))
+        h2d, d2h = env.step_observe_host_begin(ring["action_ring"][t & 1], ring["slots"][t & 1], obs_t[t & 1], vec_t[t & 1])
+        assert d2h == ring["slot_bytes"]
+        if t >= 1:
+            env.host_wait(1)
+            dec = decode_results(ring["slots"][(t - 1) & 1]["packed"], dec)
+            for k in ("status", "reward", "cost", "goals_reached", "violated", "fixed_actions"):
+                _eq(dec[k].numpy(), want[t - 1][k], f"compact t={t - 1} {k}")
+            _eq(ring["slots"][(t - 1) & 1]["shadow_goals"].numpy(), want[t - 1]["shadow_goals"], "compact shadow")
+        assert torch.equal(obs_t[t & 1], want[t]["obs"])
+    env.host_wait(0)
+    dec = decode_results(ring["slots"][(T - 1) & 1]["packed"], dec)
+    _eq(dec["reward"].numpy(), want[T - 1]["reward"], "compact last reward")
     # the synchronous form still agrees and can be mixed with the split-phase form
     env.reset()
     hb = env.make_host_buffers()
@@ -318,3 +338,21 @@ def test_gpu_fused_wide_eval_channels():
     _run_vs_oracle(sc, T=8, fused=True)
     sc = random_scenario(10, 20, 30, 40, density=(0.0, 0.2), queue_len=3, seed=78, fov=9, use_da=True, use_hp=True, num_channel=6)
     _run_vs_oracle(sc, T=12, fused=True)
+
+
+def test_gpu_packed_step_output_decodes_to_the_separate_outputs():
+    """MapfStepOut.packed from mapf_step (N <= 32 and N > 32) decodes to exactly the separate per-agent outputs."""
+    from primal_ppo_b200 import StepOut, decode_results
+    for (W, H, N) in ((512, 12, 8), (32, 24, 48)):
+        sc = random_scenario(W, H, H, N, density=(0.1, 0.3), queue_len=4, seed=W + N, unique_maps=16)
+        env = _env(sc, use_tape=False)
+        packed = torch.empty((W, N), dtype=torch.int16, device="cuda")
+        o = env._out
+        out = StepOut(status=o.status, reward=o.reward, cost=o.cost, train_valid=o.train_valid, goals_reached=o.goals_reached,
+                      violated=o.violated, shadow_goals=o.shadow_goals, fixed_actions=o.fixed_actions, packed=packed)
+        acts = random_actions(16, W, N, seed=3)
+        for t in range(16):
+            env.step(torch.from_numpy(acts[t]), out=out)
+            dec = decode_results(packed.cpu())
+            for k in ("status", "reward", "cost", "goals_reached", "violated", "fixed_actions"):
+                _eq(dec[k].numpy(), _np(getattr(out, k)), f"N={N} t={t} {k}")

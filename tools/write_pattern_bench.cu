@@ -137,6 +137,49 @@ __global__ void __launch_bounds__(256, 4) warp_chunks_prefetch(float *out, int n
         for (int k = 0; k < READS; ++k) cur[k] = nxt[k];
     }
 }
+// G: pattern D, but the f32 values are expanded into a double-buffered shared-memory tile and leave through the TMA unit
+//    (cp.async.bulk.global.shared::cta) instead of st.global.v4 — SURVEY 7.3 option (ii).  TILE bytes per bulk store.
+template <int TILE>
+__global__ void __launch_bounds__(256, 4) warp_chunks_bulk(float *out, int nchunks, int chunk_bytes, int *counter) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ uint4 lut[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *mine = dyn + (size_t)warp * (2 * TILE + 2048);
+    uint32_t *wb = reinterpret_cast<uint32_t *>(mine + 2 * TILE);
+    if (threadIdx.x < 16) {
+        const uint32_t one = 0x3f800000u, t = threadIdx.x;
+        lut[t] = make_uint4((t & 1u) ? one : 0u, (t & 2u) ? one : 0u, (t & 4u) ? one : 0u, (t & 8u) ? one : 0u);
+    }
+    for (int k = lane; k < 512; k += 32) wb[k] = 0x01020304u * (k + 1 + warp);
+    __syncthreads();
+    const int ntiles = chunk_bytes / TILE;          // chunk_bytes is a multiple of TILE
+    int issued = 0;
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(counter, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= nchunks) break;
+        char *gdst = reinterpret_cast<char *>(out) + (size_t)c * chunk_bytes;
+        for (int t = 0; t < ntiles; ++t, ++issued) {
+            unsigned char *buf = mine + (issued & 1) * TILE;
+            if (issued >= 2) {                        // the bulk store that read this buffer two tiles ago must be done reading
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+            const int sh = (lane & 7) << 2;
+            uint4 *b4 = reinterpret_cast<uint4 *>(buf);
+            for (int q = lane; q < TILE / 16; q += 32) b4[q] = lut[(wb[(t * (TILE / 16) + q) >> 3 & 511] >> sh) & 15u];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(buf);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst + (size_t)t * TILE), "r"(saddr), "r"(TILE) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 // C: plain grid-stride fill
 __global__ void fill(float *out, size_t n4) {
     const uint4 v = make_uint4(1, 2, 3, 4);
@@ -236,6 +279,21 @@ int main() {
         }
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
         cudaCtxResetPersistingL2Cache();
+    }
+    {
+        // G: smem tile + TMA bulk store, against D (same LUT expansion, st.global.v4) measured above
+        auto g = [&](auto kern, int tile, const char *label) {
+            for (int bps : {2, 3, 4}) {
+                const int sm = 8 * (2 * tile + 2048);
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+                char nm[96];
+                snprintf(nm, sizeof nm, "G smem tile %s + cp.async.bulk store, %d blk/SM", label, bps);
+                run(nm, [&] { kern<<<148 * bps, 256, sm>>>(out, nchunks, 62208, counter); });
+            }
+        };
+        g(warp_chunks_bulk<1296>, 1296, "1296 B");
+        g(warp_chunks_bulk<3888>, 3888, "3888 B");
+        g(warp_chunks_bulk<7776>, 7776, "7776 B");
     }
     for (int bps : {4, 8, 16}) {
         char nm[96];
