@@ -179,6 +179,12 @@ int mapf_bfs_refresh(MapfEnv *env, const uint8_t *goals_reached, int16_t *bfs_ma
 int mapf_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, double gamma,
              double lam, int32_t T, int64_t cols, float *returns, float *adv, void *stream);
 
+/* Both streams of the rollout in ONE launch (runner.py:146-149 calls the scan twice: rewards / values and costRewards /
+ * costValues): same arithmetic as two mapf_gae calls, bit for bit. */
+int mapf_gae2(const float *r, const float *v, const float *last_v, const float *cost_r, const float *cost_v,
+              const float *last_cost_v, const uint8_t *nonterminal, double gamma, double lam, int32_t T, int64_t cols,
+              float *returns, float *cost_returns, float *adv, float *cost_adv, void *stream);
+
 /* Joint-action sampling on device — replaces the per-agent host loop `np.random.choice(range(N_ACTIONS), p=ps[i])`
  * of Model.step / Model.evaluate (model.py:38-40, 58-59).  ps: f32 [rows,5] probabilities (rows = W*N); actions: int8
  * [rows]; chosen_p (optional): f32 [rows] probability of the drawn action.  Philox4x32-10 keyed by (seed; row, draw):
@@ -291,6 +297,39 @@ int mapf_step_observe_host_wait(MapfEnv *env, int age);
  * reference's per-agent arrays; any pointer of `out` may be NULL; out->train_valid / shadow_goals / good_actions are not
  * touched.  Bit-identical to the arrays the full format carries. */
 int mapf_decode_results_host(const uint16_t *packed, int64_t n, const MapfStepOutHost *out);
+
+/* ---- learner-side glue: the elementwise part of the PPO-Lagrangian minibatch loss ----------------------- */
+
+/* Replaces the ~40 eager tensor ops of Model.train between the network outputs and `loss.backward()` (model.py:104-164):
+ * advantage normalisation, probability ratio, clipped surrogate, clipped value / cost-value losses, entropy, valid-action
+ * loss, cost term.  Two calls per minibatch:
+ *   mapf_adv_moments: per-block partial sums [MAPF_PPO_LOSS_MAX_BLOCKS, 4] (double) of a, a^2, c, c^2 with
+ *       a = returns - old_v, c = cost_returns - old_cv (model.py:106-108); the caller adds the rows (and all-reduces them
+ *       over ranks so that every rank normalises with the GLOBAL minibatch statistics) and forms
+ *       mean / unbiased std;
+ *   mapf_ppo_loss: with those statistics, one pass over the n = rows x agents elements computing the gradients of
+ *       loss = -policy_loss - entropy_coef*entropy + value_coef*critic + valid_coef*valid + cost_value_coef*cost_critic
+ *              + cost_coef*lagrangian*cost_loss                                            (model.py:153-164)
+ *       with respect to the network outputs (g_policy [n,5], g_value [n], g_cost_value [n], g_sig [n,5]; any may be NULL)
+ *       and per-block partial sums [MAPF_PPO_LOSS_MAX_BLOCKS, MAPF_PPO_LOSS_STATS] (double):
+ *       0 surrogate, 1 entropy, 2 critic, 3 cost critic, 4 valid log-likelihood (all 5 actions), 5 ratio*cadv, 6 clipped
+ *       count, 7 advantage, 8 cost advantage.  Every mean is sum / n_global (a rank's share of the global minibatch).
+ * All pointers are device pointers; asynchronous on `stream`; the current device is used. */
+#define MAPF_PPO_LOSS_MAX_BLOCKS 1024
+#define MAPF_PPO_LOSS_STATS 10
+typedef struct MapfPpoLossConfig {
+    float clip_range, entropy_coef, value_coef, valid_coef, cost_value_coef, cost_coef; /* TrainingParameters, alg_parameters.py:53-91 */
+    float lagrangian;             /* current multiplier (lagrange.py) */
+    int32_t minus_adv_with_cadv;  /* model.py:111-113 */
+    double n_global;              /* elements (rows x agents) of the GLOBAL minibatch */
+    double adv_mean, adv_std, cadv_mean, cadv_std; /* statistics of the global minibatch (unbiased std) */
+} MapfPpoLossConfig;
+int mapf_adv_moments(const float *returns, const float *cost_returns, const float *old_v, const float *old_cv, int64_t n,
+                     double *partials, void *stream);
+int mapf_ppo_loss(const MapfPpoLossConfig *cfg, int64_t n, const float *policy, const float *value, const float *cost_value,
+                  const float *policy_sig, const float *returns, const float *cost_returns, const float *old_v,
+                  const float *old_cv, const int8_t *actions, const float *old_ps, const float *train_valid, float *g_policy,
+                  float *g_value, float *g_cost_value, float *g_sig, double *partials, void *stream);
 
 /* ---- integrity helper ------------------------------------------------------------------------------------------------- */
 

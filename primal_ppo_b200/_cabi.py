@@ -11,11 +11,11 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libmapf_b200.so")
 
 EXPORTED = ["mapf_abi_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_reset", "mapf_evaluate",
-            "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae",
+            "mapf_joint_step", "mapf_step", "mapf_observe", "mapf_bfs", "mapf_bfs_refresh", "mapf_gae", "mapf_gae2",
             "mapf_get_state", "mapf_get_counters", "mapf_step_observe_host", "mapf_step_observe",
             "mapf_sample_actions", "mapf_generate_scenario",
             "mapf_observe_bf16", "mapf_step_observe_bf16", "mapf_state_bytes", "mapf_save_state", "mapf_load_state",
-            "mapf_get_human", "mapf_host_layout", "mapf_step_observe_host_begin", "mapf_step_observe_host_wait", "mapf_decode_results_host", "mapf_checksum_rows"]
+            "mapf_get_human", "mapf_host_layout", "mapf_step_observe_host_begin", "mapf_step_observe_host_wait", "mapf_decode_results_host", "mapf_checksum_rows", "mapf_adv_moments", "mapf_ppo_loss"]
 ABI_VERSION = 2
 
 ERR_NO_VIABLE, ERR_FIX_ITER_CAP, ERR_BAD_ACTION, ERR_TAPE, ERR_NO_FREE_CELL = 1, 2, 4, 8, 64
@@ -59,6 +59,16 @@ class MapfHostLayout(C.Structure):
 HOST_TRAIN_VALID, HOST_COMPACT = 1, 2
 
 
+class MapfPpoLossConfig(C.Structure):
+    _fields_ = [("clip_range", C.c_float), ("entropy_coef", C.c_float), ("value_coef", C.c_float), ("valid_coef", C.c_float),
+                ("cost_value_coef", C.c_float), ("cost_coef", C.c_float), ("lagrangian", C.c_float),
+                ("minus_adv_with_cadv", C.c_int32), ("n_global", C.c_double), ("adv_mean", C.c_double),
+                ("adv_std", C.c_double), ("cadv_mean", C.c_double), ("cadv_std", C.c_double)]
+
+
+PPO_LOSS_MAX_BLOCKS, PPO_LOSS_STATS = 1024, 10
+
+
 class MapfError(RuntimeError):
     pass
 
@@ -91,6 +101,9 @@ def load_library():
     lib.mapf_bfs.argtypes = [vp, vp, i64, vp, vp]
     lib.mapf_bfs_refresh.argtypes = [vp, vp, vp, vp]
     lib.mapf_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, i32, i64, vp, vp, vp]
+    lib.mapf_gae2.argtypes = [vp] * 7 + [C.c_double, C.c_double, i32, i64, vp, vp, vp, vp, vp]
+    lib.mapf_adv_moments.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    lib.mapf_ppo_loss.argtypes = [C.POINTER(MapfPpoLossConfig), i64] + [vp] * 17
     lib.mapf_sample_actions.argtypes = [vp, i64, C.c_uint64, C.c_uint32, vp, vp, vp]
     lib.mapf_generate_scenario.argtypes = [C.POINTER(MapfGenConfig)] + [vp] * 9
     lib.mapf_state_bytes.argtypes = [vp]

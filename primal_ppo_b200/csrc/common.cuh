@@ -250,6 +250,17 @@ cudaError_t launch_arrivals(const EnvView &v, const uint8_t *goals, int32_t *lis
 cudaError_t launch_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, float g, float gl,
                        int T, long long cols, float *ret, float *adv, cudaStream_t s);
 
+cudaError_t launch_gae2(const float *r, const float *v, const float *last_v, const float *cr, const float *cv,
+                        const float *last_cv, const uint8_t *nonterminal, float g, float gl, int T, long long cols, float *ret,
+                        float *cret, float *adv, float *cadv, cudaStream_t s);
+
+cudaError_t launch_adv_moments(const float *ret, const float *cret, const float *old_v, const float *old_cv, long long n,
+                               double *partials, cudaStream_t s);
+cudaError_t launch_ppo_loss(const MapfPpoLossConfig &cfg, long long n, const float *policy, const float *value,
+                            const float *cost_value, const float *sig, const float *ret, const float *cret, const float *old_v,
+                            const float *old_cv, const int8_t *actions, const float *old_ps, const float *tv, float *g_policy,
+                            float *g_value, float *g_cost_value, float *g_sig, double *partials, cudaStream_t s);
+
 cudaError_t launch_sample_actions(const float *ps, long long rows, unsigned long long seed, uint32_t draw, int8_t *actions,
                                   float *chosen_p, cudaStream_t s);
 

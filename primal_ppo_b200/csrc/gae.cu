@@ -7,6 +7,8 @@
 // NumPy rounds every *, +, - separately in f32, so the kernel uses __fmul_rn/__fadd_rn/__fsub_rn (never contracted
 // into FMA) and is bit-exact with the reference.  Thread = 4 adjacent columns (one column = one (world, agent) pair),
 // serial over t = T-1..0 with the loads of 8 time steps in flight; 12 B of HBM traffic per element and stream.
+// The rollout has two streams (rewards/values and costRewards/costValues, runner.py:146-149): mapf_gae2 scans both in ONE
+// launch (blockIdx.y = stream), which doubles the columns in flight and halves the launch / tail overhead.
 #include "common.cuh"
 
 namespace mapf {
@@ -33,13 +35,20 @@ __device__ __forceinline__ void store(float *p, const float (&o)[V]) {
     else __stcs(p, o[0]);
 }
 
+struct GaeStream {
+    const float *r, *v, *last_v;
+    float *ret, *adv;
+};
+
 template <int V>
 __global__ void __launch_bounds__(128)
-gae_kernel(const float *__restrict__ r, const float *__restrict__ v, const float *__restrict__ last_v,
-           const uint8_t *__restrict__ nonterminal, const float g, const float gl, const int T, const long long cols,
-           float *__restrict__ ret, float *__restrict__ adv) {
+gae_kernel(const GaeStream s0, const GaeStream s1, const uint8_t *__restrict__ nonterminal, const float g, const float gl,
+           const int T, const long long cols) {
     const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (col >= cols) return;
+    const GaeStream &S = blockIdx.y ? s1 : s0;
+    const float *__restrict__ r = S.r, *__restrict__ v = S.v, *__restrict__ last_v = S.last_v;
+    float *__restrict__ ret = S.ret, *__restrict__ adv = S.adv;
     float nv[V], last[V];
     load<V>(last_v + col, nv);
 #pragma unroll
@@ -84,18 +93,29 @@ gae_kernel(const float *__restrict__ r, const float *__restrict__ v, const float
 
 }  // namespace
 
-cudaError_t launch_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, float g, float gl,
-                       int T, long long cols, float *ret, float *adv, cudaStream_t stream) {
+cudaError_t launch_gae2(const float *r, const float *v, const float *last_v, const float *cr, const float *cv,
+                        const float *last_cv, const uint8_t *nonterminal, float g, float gl, int T, long long cols, float *ret,
+                        float *cret, float *adv, float *cadv, cudaStream_t stream) {
     if (cols <= 0 || T <= 0) return cudaSuccess;
     auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    const bool vec = (cols % 4 == 0) && al(r) && al(v) && al(last_v) && al(ret) && (adv == nullptr || al(adv));
+    const bool two = cr != nullptr;
+    bool vec = (cols % 4 == 0) && al(r) && al(v) && al(last_v) && al(ret) && (adv == nullptr || al(adv));
+    if (two) vec = vec && al(cr) && al(cv) && al(last_cv) && al(cret) && (cadv == nullptr || al(cadv));
+    const GaeStream s0{r, v, last_v, ret, adv}, s1{cr, cv, last_cv, cret, cadv};
     if (vec) {
         const long long threads = cols / 4;
-        gae_kernel<4><<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(r, v, last_v, nonterminal, g, gl, T, cols, ret, adv);
+        const dim3 grid((unsigned)((threads + 127) / 128), two ? 2 : 1);
+        gae_kernel<4><<<grid, 128, 0, stream>>>(s0, s1, nonterminal, g, gl, T, cols);
     } else {
-        gae_kernel<1><<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(r, v, last_v, nonterminal, g, gl, T, cols, ret, adv);
+        const dim3 grid((unsigned)((cols + 127) / 128), two ? 2 : 1);
+        gae_kernel<1><<<grid, 128, 0, stream>>>(s0, s1, nonterminal, g, gl, T, cols);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_gae(const float *r, const float *v, const float *last_v, const uint8_t *nonterminal, float g, float gl,
+                       int T, long long cols, float *ret, float *adv, cudaStream_t stream) {
+    return launch_gae2(r, v, last_v, nullptr, nullptr, nullptr, nonterminal, g, gl, T, cols, ret, nullptr, adv, nullptr, stream);
 }
 
 }  // namespace mapf

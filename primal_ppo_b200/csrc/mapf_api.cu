@@ -366,6 +366,37 @@ int mapf_gae(const float *r, const float *v, const float *last_v, const uint8_t 
     return MAPF_OK;
 }
 
+int mapf_gae2(const float *r, const float *v, const float *last_v, const float *cr, const float *cv, const float *last_cv,
+              const uint8_t *nonterminal, double gamma, double lam, int32_t T, int64_t cols, float *returns, float *cost_returns,
+              float *adv, float *cost_adv, void *stream) {
+    if (!r || !v || !last_v || !returns || !cr || !cv || !last_cv || !cost_returns) return fail(MAPF_E_NULL, "mapf_gae2: null argument");
+    if (T < 0 || cols < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_gae2: negative size");
+    const float g = (float)(gamma * 1.0), gl = (float)(gamma * lam * 1.0);
+    CU(launch_gae2(r, v, last_v, cr, cv, last_cv, nonterminal, g, gl, T, cols, returns, cost_returns, adv, cost_adv, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_adv_moments(const float *returns, const float *cost_returns, const float *old_v, const float *old_cv, int64_t n,
+                     double *partials, void *stream) {
+    if (!returns || !cost_returns || !old_v || !old_cv || !partials) return fail(MAPF_E_NULL, "mapf_adv_moments: null argument");
+    if (n < 0) return fail(MAPF_E_BAD_CONFIG, "mapf_adv_moments: n < 0");
+    CU(launch_adv_moments(returns, cost_returns, old_v, old_cv, n, partials, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
+int mapf_ppo_loss(const MapfPpoLossConfig *cfg, int64_t n, const float *policy, const float *value, const float *cost_value,
+                  const float *policy_sig, const float *returns, const float *cost_returns, const float *old_v,
+                  const float *old_cv, const int8_t *actions, const float *old_ps, const float *train_valid, float *g_policy,
+                  float *g_value, float *g_cost_value, float *g_sig, double *partials, void *stream) {
+    if (!cfg || !policy || !value || !cost_value || !policy_sig || !returns || !cost_returns || !old_v || !old_cv || !actions ||
+        !old_ps || !train_valid || !partials)
+        return fail(MAPF_E_NULL, "mapf_ppo_loss: null argument");
+    if (n < 0 || !(cfg->n_global > 0)) return fail(MAPF_E_BAD_CONFIG, "mapf_ppo_loss: n >= 0 and n_global > 0 required");
+    CU(launch_ppo_loss(*cfg, n, policy, value, cost_value, policy_sig, returns, cost_returns, old_v, old_cv, actions, old_ps,
+                       train_valid, g_policy, g_value, g_cost_value, g_sig, partials, (cudaStream_t)stream));
+    return MAPF_OK;
+}
+
 int mapf_sample_actions(const float *ps, int64_t rows, uint64_t seed, uint32_t draw, int8_t *actions, float *chosen_p,
                         void *stream) {
     if (!ps || !actions) return fail(MAPF_E_NULL, "mapf_sample_actions: null argument");

@@ -28,10 +28,13 @@ from .policy import ScrimpPolicy
 class PPOLearner:
     """`Model(global_model=True)` (`model.py:16-24`): network + Adam + Lagrange multiplier, data-parallel over `group`."""
 
-    def __init__(self, policy: ScrimpPolicy, cfg: PPOConfig = PPOConfig(), group=None, amp_dtype=None):
+    def __init__(self, policy: ScrimpPolicy, cfg: PPOConfig = PPOConfig(), group=None, amp_dtype=None, fused_loss=None):
+        """fused_loss: compute the elementwise part of the loss and its gradients with the fused CUDA kernel
+        (`fused_loss.py`, `csrc/ppo_loss.cu`) instead of the eager PyTorch statement in `loss.py`; default: on CUDA."""
         self.policy, self.cfg, self.group, self.amp_dtype = policy, cfg, group, amp_dtype
         self.params = [p for p in policy.parameters() if p.requires_grad]
         dev = self.params[0].device
+        self.fused_loss = (dev.type == "cuda") if fused_loss is None else bool(fused_loss)
         n = sum(p.numel() for p in self.params)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
@@ -48,7 +51,11 @@ class PPOLearner:
         with torch.autocast(dev_type, dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             out = self.policy(batch["obs"], batch["vec"])
         out = type(out)(*[o.float() for o in out])
-        loss, stats = ppo_lagrange_loss(out, returns=batch["returns"], cost_returns=batch["cost_returns"],
+        if self.fused_loss:
+            from .fused_loss import fused_ppo_lagrange_loss as loss_fn
+        else:
+            loss_fn = ppo_lagrange_loss
+        loss, stats = loss_fn(out, returns=batch["returns"], cost_returns=batch["cost_returns"],
                                         old_v=batch["values"], old_cv=batch["cost_values"], actions=batch["actions"],
                                         old_ps=batch["ps"], train_valid=batch["train_valid"],
                                         lagrangian=self.lagrange.value(), cfg=self.cfg, group=self.group)
@@ -183,7 +190,7 @@ class VecPPOTrainer:
     @torch.no_grad()
     def collect(self) -> Dict[str, float]:
         """`Runner.run` (`runner.py:28-150`) for all worlds at once."""
-        from ..vec_env import StepOut, gae, sample_actions
+        from ..vec_env import StepOut, gae2, sample_actions
         b, env = self.buf, self.env
         if self.fresh_worlds is not None and self.rollouts > 0:
             env.reset(self.fresh_worlds(self.rollouts))
@@ -201,8 +208,8 @@ class VecPPOTrainer:
             env.step_observe(b.actions[t], out=out, obs_out=(b.obs[t + 1], b.vec[t + 1]))
         last_v = torch.empty_like(b.values[0]); last_cv = torch.empty_like(b.values[0])
         self._forward(b.obs[self.T], b.vec[self.T], None, last_v, last_cv)
-        b.returns = gae(b.rewards, b.values, last_v, self.cfg.gamma, self.cfg.lam)
-        b.cost_returns = gae(b.cost_rewards, b.cost_values, last_cv, self.cfg.gamma, self.cfg.lam)
+        b.returns, b.cost_returns = gae2(b.rewards, b.values, last_v, b.cost_rewards, b.cost_values, last_cv,
+                                         self.cfg.gamma, self.cfg.lam)          # both streams, one launch
         # OneEpPerformance means over worlds (driver.py:101-112)
         perf = dict(episodeReward=float(b.rewards.sum(dim=(0, 2)).mean()),
                     episodeCostReward=float(b.cost_rewards.sum(dim=(0, 2)).mean()),

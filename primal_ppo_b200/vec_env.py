@@ -562,6 +562,28 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, last_values: torch.Tensor, 
     return (ret, adv) if return_advantages else ret
 
 
+def gae2(rewards, values, last_values, cost_rewards, cost_values, last_cost_values, gamma: float = 0.95, lam: float = 0.95,
+         nonterminal: Optional[torch.Tensor] = None):
+    """Both GAE streams of a rollout in one launch (``mapf_gae2``; runner.py:146-149): returns (returns, cost_returns),
+    bit-identical to two ``gae`` calls."""
+    lib = _cabi.load_library()
+    ts = [x.contiguous().to(torch.float32) for x in (rewards, values, last_values, cost_rewards, cost_values, last_cost_values)]
+    r, v, lv, cr, cv, lcv = ts
+    assert r.is_cuda and v.shape == r.shape and cr.shape == r.shape and cv.shape == r.shape
+    T = int(r.shape[0])
+    cols = r.numel() // max(T, 1) if T else 0
+    assert lv.numel() == cols and lcv.numel() == cols
+    ret, cret = torch.empty_like(r), torch.empty_like(r)
+    if r.numel() == 0:
+        return ret, cret
+    nt = None if nonterminal is None else nonterminal.to(torch.uint8).contiguous()
+    stream = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+    with torch.cuda.device(r.device):
+        _cabi.check(lib.mapf_gae2(_ptr(r), _ptr(v), _ptr(lv), _ptr(cr), _ptr(cv), _ptr(lcv), _ptr(nt), float(gamma), float(lam),
+                                  T, cols, _ptr(ret), _ptr(cret), None, None, stream), "mapf_gae2")
+    return ret, cret
+
+
 def sample_actions(ps: torch.Tensor, seed: int = 1234, draw: int = 0, out: Optional[torch.Tensor] = None,
                    chosen_p: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Joint-action sampling on device (model.py:38-40): ps f32 [..., 5] -> int8 [...] actions."""

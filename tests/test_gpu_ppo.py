@@ -160,3 +160,104 @@ def test_gpu_policy_fused_conv_relu_path_equals_plain_path():
         tol = 1e-5 if dt is None else 2e-2
         assert float((a.policy.float() - b.policy.detach().float()).abs().max()) < tol
         assert float((a.value.float() - b.value.detach().float()).abs().max()) < tol * 10
+
+
+def test_gpu_gae2_both_streams_one_launch_bit_exact():
+    """mapf_gae2 (both rollout streams in one launch) = two mapf_gae calls = the oracle, bit for bit."""
+    import numpy as np
+    from oracle import gae_oracle
+    from primal_ppo_b200 import gae, gae2
+    rng = np.random.default_rng(3)
+    for T, cols in ((64, 4096), (7, 33), (256, 8 * 32)):
+        a = [rng.normal(size=(T, cols)).astype(np.float32) for _ in range(4)]
+        lv, lcv = (rng.normal(size=(cols,)).astype(np.float32) for _ in range(2))
+        t = lambda x: torch.from_numpy(x).cuda()
+        ret, cret = gae2(t(a[0]), t(a[1]), t(lv), t(a[2]), t(a[3]), t(lcv))
+        assert torch.equal(ret, gae(t(a[0]), t(a[1]), t(lv))) and torch.equal(cret, gae(t(a[2]), t(a[3]), t(lcv)))
+        assert ret.cpu().numpy().tobytes() == gae_oracle(a[0], a[1], lv)[0].tobytes()
+        assert cret.cpu().numpy().tobytes() == gae_oracle(a[2], a[3], lcv)[0].tobytes()
+
+
+@pytest.mark.parametrize("variant", ["default", "cost_terms", "no_mix"])
+def test_gpu_fused_ppo_loss_matches_pytorch_loss_values_and_gradients(variant):
+    """The fused elementwise loss kernel (csrc/ppo_loss.cu) against ppo/loss.py (the PyTorch restatement of model.py:104-164
+    that tests/test_ppo_parity.py pins to the reference): loss, every statistic, and the gradients with respect to all four
+    network outputs.  fp32; tolerance 2e-5 relative to the largest gradient element, 1e-5 + 1e-5*|x| on the statistics."""
+    from primal_ppo_b200.ppo.fused_loss import fused_ppo_lagrange_loss
+    from primal_ppo_b200.ppo.loss import PPOConfig, ppo_lagrange_loss
+    from primal_ppo_b200.ppo.policy import PolicyOutput
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, N = 96, 32
+    cfg = {"default": PPOConfig(), "cost_terms": PPOConfig(cost_value_coef=0.05, cost_coef=0.2),
+           "no_mix": PPOConfig(minus_adv_with_cadv=False, cost_coef=0.3, cost_value_coef=0.1)}[variant]
+    lag = 0.7
+
+    def inputs():
+        logits = torch.randn((B, N, 5), generator=g, device="cuda")
+        policy = torch.softmax(logits, -1)
+        policy[0, 0] = torch.tensor([1.0, 0, 0, 0, 0], device="cuda")          # exercises the clamps
+        value = torch.randn((B, N, 1), generator=g, device="cuda")
+        cost_value = torch.randn((B, N, 1), generator=g, device="cuda")
+        sig = torch.sigmoid(3 * torch.randn((B, N, 5), generator=g, device="cuda"))
+        sig[0, 1, 0] = 1.0; sig[0, 1, 1] = 0.0
+        return [x.requires_grad_(True) for x in (policy, value, cost_value, sig)]
+    data = dict(returns=torch.randn((B, N), generator=g, device="cuda"), cost_returns=torch.randn((B, N), generator=g, device="cuda"),
+                old_v=torch.randn((B, N), generator=g, device="cuda"), old_cv=torch.randn((B, N), generator=g, device="cuda"),
+                actions=torch.randint(0, 5, (B, N), generator=g, device="cuda", dtype=torch.int8),
+                old_ps=torch.softmax(torch.randn((B, N, 5), generator=g, device="cuda"), -1),
+                train_valid=(torch.rand((B, N, 5), generator=g, device="cuda") < 0.6).float())
+    data["old_v"][1] = data["returns"][1] + 0.01                              # values inside and outside the clip range
+    leaves = inputs()
+    clones = [x.detach().clone().requires_grad_(True) for x in leaves]
+
+    def run(fn, xs):
+        kw = {f: None for f in PolicyOutput._fields}
+        kw.update(policy=xs[0], value=xs[1], cost_value=xs[2], policy_sig=xs[3])
+        out = PolicyOutput(**kw)
+        loss, stats = fn(out, lagrangian=lag, cfg=cfg, group=None, **data)
+        loss.backward()
+        return loss, stats
+    l1, s1 = run(ppo_lagrange_loss, leaves)
+    l2, s2 = run(fused_ppo_lagrange_loss, clones)
+    assert abs(float(l1) - float(l2)) <= 1e-5 + 1e-5 * abs(float(l1)), (float(l1), float(l2))
+    for k in s1:
+        a, b = float(s1[k]), float(s2[k])
+        assert abs(a - b) <= 1e-5 + 1e-5 * abs(a), (k, a, b)
+    for x, y, name in zip(leaves, clones, ("policy", "value", "cost_value", "policy_sig")):
+        scale = float(x.grad.abs().max())
+        if scale == 0.0:
+            assert float(y.grad.abs().max()) == 0.0, name
+            continue
+        err = float((x.grad - y.grad).abs().max())
+        assert err <= 2e-5 * scale, (name, err, scale)
+
+
+def test_gpu_learner_with_fused_loss_equals_learner_with_pytorch_loss():
+    """PPOLearner end to end (forward, loss, backward, flat gradient): fused kernel vs eager loss, same weights, fp32."""
+    from primal_ppo_b200.ppo import PPOConfig, ScrimpPolicy
+    from primal_ppo_b200.ppo.trainer import PPOLearner
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, N = 8, 16
+    batch = dict(obs=(torch.rand((B, N, 6, 9, 9), generator=g, device="cuda") < 0.2).float(),
+                 vec=torch.randn((B, N, 4), generator=g, device="cuda"), returns=torch.randn((B, N), generator=g, device="cuda"),
+                 cost_returns=torch.randn((B, N), generator=g, device="cuda"), values=torch.randn((B, N), generator=g, device="cuda"),
+                 cost_values=torch.randn((B, N), generator=g, device="cuda"),
+                 actions=torch.randint(0, 5, (B, N), generator=g, device="cuda", dtype=torch.int8),
+                 ps=torch.softmax(torch.randn((B, N, 5), generator=g, device="cuda"), -1),
+                 train_valid=(torch.rand((B, N, 5), generator=g, device="cuda") < 0.6).float())
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        grads, stats = [], []
+        for fused in (False, True):
+            torch.manual_seed(3)
+            pol = ScrimpPolicy().cuda().eval()
+            lr = PPOLearner(pol, PPOConfig(cost_value_coef=0.05, cost_coef=0.2), fused_loss=fused)
+            stats.append(lr.compute_gradients(batch))
+            grads.append(lr.flat_grad.clone())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    scale = float(grads[0].abs().max())
+    assert float((grads[0] - grads[1]).abs().max()) <= 5e-5 * scale
+    for k in stats[0]:
+        assert abs(stats[0][k] - stats[1][k]) <= 1e-5 + 1e-4 * abs(stats[0][k]), k
