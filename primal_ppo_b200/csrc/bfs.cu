@@ -186,7 +186,15 @@ bfs_gray_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const l
     uint32_t *pl = planes_all + (size_t)warp * (NB + 2) * NWL * 32 + lane;
     const long long n_maps = n_dev ? (long long)*n_dev : n_maps_in;
     const int cell0 = gl * NWL * 32;                                  // first cell of this lane's words
-
+    // The level loop is bound by the ALU pipe (shifts and logic ops issue at half rate; ncu: ALU pipe 90 %, FMA pipe 8 %
+    // busy), so the operations that have an exact integer multiply-add form are moved to the idle FMA pipe one for one:
+    //   fm &= ~nw   ->  fm = nw * 0xffffffff + fm     (nw is a subset of fm: subtracting clears exactly those bits)
+    //   edge-lane selects  ->  multiplication by 0 / 1
+    // The multipliers live in opaque registers so that the compiler does not turn them back into logic ops.  Measured
+    // (profiles/r02_bfs_variants_ab.txt): 40x40 -6 %, 80x80 -13 %, 128x128 -8 %.  Two-for-one replacements lose: shifts as
+    // hi * 2^s + mulhi(lo, 2^s) were 3 % slower at 40x40, the any-flag as a mad.wide sum 5 % slower.
+    uint32_t minus1 = 0xffffffffu, keep_prev = gl != 0 ? 1u : 0u, keep_next = gl != G - 1 ? 1u : 0u;
+    asm volatile("" : "+r"(minus1), "+r"(keep_prev), "+r"(keep_next));
     // masks of the cells that are not in column 0 / not in column Wd-1 (the +-1 shifts must not wrap between rows)
     uint32_t nc0[NWL], ncl[NWL];
 #pragma unroll
@@ -231,8 +239,8 @@ bfs_gray_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const l
             for (int t = 0; t <= WO; ++t) {
                 pv[t] = __shfl_up_sync(FULL, fr[NWL - 1 - t], 1, G);
                 nx_[t] = __shfl_down_sync(FULL, fr[t], 1, G);
-                if (gl == 0) pv[t] = 0;
-                if (gl == G - 1) nx_[t] = 0;
+                pv[t] *= keep_prev;                                   // lane 0 / G-1 of a map have no neighbour: x * 0 (FMA pipe)
+                nx_[t] *= keep_next;
             }
             auto word = [&](int idx) -> uint32_t {                    // idx is a compile-time constant after unrolling
                 if (idx >= 0 && idx < NWL) return fr[idx];
@@ -262,7 +270,10 @@ bfs_gray_kernel(const EnvView v, const int32_t *__restrict__ agent_list, const l
                 for (int j = 0; j < NWL; ++j) pb[j * 32] ^= fm[j];
             }
 #pragma unroll
-            for (int j = 0; j < NWL; ++j) { fr[j] = nw[j]; fm[j] &= ~nw[j]; }
+            for (int j = 0; j < NWL; ++j) {
+                fr[j] = nw[j];
+                fm[j] = nw[j] * minus1 + fm[j];                       // = fm & ~nw (nw is a subset of fm), on the FMA pipe
+            }
             level = nl;
         }
         // planes in use: those of codes up to `level` (warp-uniform: the loop runs until the slowest map is done)
@@ -450,6 +461,7 @@ cudaError_t launch_bfs(const EnvView &v, const int32_t *agent_list, long long n,
         int G, NWL, WO;
         const bool vec_ok = ((v.H * v.Wd) % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
         if (vec_ok && !(v.dbg_flags & (1 << 16)) && bfs_gray_shape(v, G, NWL, WO)) {
+            // row shifts as integer multiply-adds (FMA pipe) unless Wd is a multiple of 32; MAPF_DBG_FLAGS bit 21 = funnel shifts
 #define GCASE(nwl, wo) if (NWL == nwl && WO == wo) return launch_bfs_gray_t<nwl, wo>(v, agent_list, n, n_dev, out, G, scatter, work_counter, stream);
 #define GCASES0(nwl) GCASE(nwl, 0)
 #define GCASES1(nwl) GCASES0(nwl) GCASE(nwl, 1)
