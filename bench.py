@@ -727,6 +727,20 @@ def main():
         gae_bytes = 12.0 * T * cols
         line_extra["gae"] = {"T": T, "cols": cols, "ms": gae_ms, "elements_per_s": T * cols / (gae_ms * 1e-3),
                              "achieved_gbs": gae_bytes / (gae_ms * 1e-3) / 1e9, "frac": gae_bytes / (gae_ms * 1e-3) / 1e9 / peak}
+        try:                      # both rollout streams (rewards / values, costRewards / costValues) in ONE launch: mapf_gae2
+            from primal_ppo_b200 import gae2
+            cr = torch.randn((T, cols), device=dev); cv = torch.randn((T, cols), device=dev)
+            gae2(r, v, lv, cr, cv, lv); torch.cuda.synchronize(dev)
+            a.record()
+            for _ in range(3):
+                gae2(r, v, lv, cr, cv, lv)
+            b.record(); torch.cuda.synchronize(dev)
+            g2 = a.elapsed_time(b) / 3
+            line_extra["gae"].update(two_streams_ms=g2, two_streams_gbs=2 * gae_bytes / (g2 * 1e-3) / 1e9,
+                                     two_streams_frac=2 * gae_bytes / (g2 * 1e-3) / 1e9 / peak)
+            del cr, cv
+        except Exception as ex:
+            line_extra["gae"]["two_streams_error"] = str(ex)[:200]
         del r, v, lv
         # optional bf16 observation format (same values, half the bytes; not the reference layout, not the headline)
         try:
