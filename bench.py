@@ -399,6 +399,8 @@ def cpu_port_throughput(budget_s, worlds, threads, seed=7):
 def python_reference(budget_s):
     """The UNMODIFIED Python reference env (baseline/_ref, installed by baseline/install_ref.py where /root/reference exists)
     timed on this box's host cores, one process per core: BASELINE configs[2]'s shape and configs[0]."""
+    if budget_s <= 0:
+        return {"skipped": "--python-ref-budget 0"}
     try:
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         import cpu_baseline
