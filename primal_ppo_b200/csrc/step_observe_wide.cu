@@ -116,8 +116,21 @@ WidePlan make_plan(const EnvView &v, int out_bf16, int FW_WARPS) {
     size_t budget = staged < 36 * 1024 ? (36 * 1024 - staged) / FW_WARPS : 0;
     if (budget > 12 * 1024) budget = 12 * 1024;
     auto per_warp_bytes = [&](int ch) { return (size_t)ch * ((PB + 31) / 32 + 2) * 4 * 2; };
-    int CH = 32;
-    while (CH > 2 && ((v.N + CH - 1) / CH < FW_WARPS || per_warp_bytes(CH) > 12 * 1024 || (CH > 8 && per_warp_bytes(CH) > budget))) CH >>= 1;
+    // Balanced chunks: with `r` rounds every warp builds r chunks of CH = ceil(N / (warps * r)) agents, rounded up so that a
+    // chunk's block stays 16-byte aligned (vector stores); the smallest r whose scratch fits the budget wins.  (Power-of-two
+    // chunks left 33 agents as 5 chunks of 8 on 4 warps — one warp with twice the work — and 48 agents as 6.)
+    const int need_al = out_bf16 ? 8 : 4;
+    int g = need_al;
+    while (g > 1 && PB % g) g >>= 1;
+    const int mult = need_al / g;                                   // CH must be a multiple of this
+    int CH = 0;
+    for (int r = 1; r <= 64 && CH == 0; ++r) {
+        int ch = (v.N + FW_WARPS * r - 1) / (FW_WARPS * r);
+        ch = (ch + mult - 1) / mult * mult;
+        if (ch > 32) continue;
+        if (per_warp_bytes(ch) <= 12 * 1024 && (ch <= 8 || per_warp_bytes(ch) <= budget)) CH = ch;
+    }
+    if (CH == 0) CH = mult <= 2 ? 2 : mult;
     if (per_warp_bytes(CH) > 28 * 1024) return p;
     p.L = make_layout(v.HP, v.RW, v.GS, v.N, v.C, v.F, CH);
     p.L.alias = 0;
@@ -151,7 +164,9 @@ cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, co
     int variant = (v.dbg_flags >> 24) & 3;
     if (variant == 0) {
         const WidePlan p4 = make_plan(v, out_bf16, 4);
-        variant = (p4.ok && p4.smem <= 40 * 1024) ? 2 : 1;
+        // ... and eight of them (compiled for 64 registers) when eight fit: mid-size worlds (33..100 agents) have a short
+        // store phase per world, so they need even more worlds in flight (40x40x64: 0.771 vs 0.806 ms; 80x80x64: 0.384 vs 0.406)
+        variant = !(p4.ok && p4.smem <= 40 * 1024) ? 1 : (p4.smem <= 28 * 1024 ? 3 : 2);
     }
     const int warps = variant == 1 ? 8 : 4;
     WidePlan p = make_plan(v, out_bf16, warps);
