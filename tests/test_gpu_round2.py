@@ -396,3 +396,36 @@ def test_gpu_outputs_stay_inside_their_buffers(shape):
         assert bool((raw[:G] == 0xA5).all()) and bool((raw[-G:] == 0xA5).all()), f"{k}: a store landed outside the buffer"
         assert not bool((views[k].view(torch.uint8) == 0xA5).all()), f"{k}: never written"
     assert not _np(env.state()["err"]).any() or True
+
+
+def test_gpu_env_on_another_device_than_the_current_one():
+    """Every entry point runs on the env's own device whatever the caller's current device is, and leaves the caller's current
+    device untouched (mapf_api.cu DeviceGuard).  Needs two GPUs; skipped on a one-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = random_scenario(64, 20, 20, 8, density=(0.1, 0.25), queue_len=3, seed=21)
+    acts = random_actions(6, 64, 8, seed=22)
+    torch.cuda.set_device(0)
+    e0 = _env(sc, device="cuda:0", use_tape=False, seed=3)
+    e1 = _env(sc, device="cuda:1", use_tape=False, seed=3)          # created while cuda:0 is current
+    assert torch.cuda.current_device() == 0
+    ring = e1.make_host_ring(compact=True)
+    for t in range(6):
+        a = torch.from_numpy(acts[t])
+        o0, obs0, vec0 = e0.step_observe(a)
+        o1, obs1, vec1 = e1.step_observe(a)                         # cuda:1 env driven with cuda:0 current
+        assert torch.cuda.current_device() == 0
+        assert obs1.device.index == 1 and torch.equal(obs0.cpu(), obs1.cpu()) and torch.equal(vec0.cpu(), vec1.cpu())
+        for k in ("status", "reward", "cost", "train_valid", "goals_reached", "violated", "shadow_goals", "fixed_actions"):
+            assert torch.equal(getattr(o0, k).cpu(), getattr(o1, k).cpu()), (t, k)
+    assert torch.equal(e0.bfs_maps().cpu(), e1.bfs_maps().cpu())
+    assert torch.equal(e0.allGoodActions.cpu(), e1.allGoodActions.cpu())
+    assert torch.equal(e0.counters().cpu(), e1.counters().cpu())
+    ring["action_ring"][0].copy_(torch.from_numpy(acts[0]))
+    obs1 = torch.empty((64, 8, 6, 9, 9), device="cuda:1"); vec1 = torch.empty((64, 8, 4), device="cuda:1")
+    e1.step_observe_host_begin(ring["action_ring"][0], ring["slots"][0], obs1, vec1)
+    e1.host_wait(0)
+    o0, _, _ = e0.step_observe(torch.from_numpy(acts[0]))
+    from primal_ppo_b200 import decode_results
+    _eq(decode_results(ring["slots"][0]["packed"])["reward"].numpy(), _np(o0.reward), "host call on cuda:1")
+    assert torch.cuda.current_device() == 0
