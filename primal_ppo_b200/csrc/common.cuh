@@ -29,6 +29,28 @@ constexpr unsigned FULL = 0xffffffffu;
 // status codes of getActionStatus (mapf_gym.py:440-444)
 constexpr int ST_STATIC = -1, ST_HUMAN = -2, ST_AGENT = -3, ST_REPEAT = -4, ST_OK = 1;
 
+// A lane group: G consecutive lanes of a warp that own one world (lane within the group = agent).  G = 32 is the whole warp
+// (one world per warp); G = 8 / 16 pack four / two small worlds into a warp (BASELINE configs[1]: 8 agents per world).  All
+// warp-level primitives take the group's lane mask, so the groups of a warp may diverge from one another freely.
+template <int G>
+struct Grp {
+    int gl;          // lane within the group (= agent index)
+    int base;        // first lane of the group
+    unsigned mask;   // lanes of the group
+    __device__ __forceinline__ explicit Grp(int lane)
+        : gl(G == 32 ? lane : lane % G), base(G == 32 ? 0 : lane / G * G),
+          mask(G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (lane / G * G))) {}
+    __device__ __forceinline__ unsigned ballot(bool p) const {                   // bit i = lane i OF THE GROUP
+        const unsigned b = __ballot_sync(mask, p);
+        return G == 32 ? b : ((b >> base) & ((1u << (G & 31)) - 1u));
+    }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    __device__ __forceinline__ uint32_t shfl(uint32_t x, int k) const { return __shfl_sync(mask, x, base + k); }
+    __device__ __forceinline__ int shfl(int x, int k) const { return __shfl_sync(mask, x, base + k); }
+    __device__ __forceinline__ uint32_t reduce_or(uint32_t x) const { return __reduce_or_sync(mask, x); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
 struct EnvView {
     int W, H, Wd, N, F, C, use_da, use_hp, Q, L, TL, hp5_per_tick;
     int P;        // padding of the shared-memory bit rows / the agent-id grid = max(2, F/2)

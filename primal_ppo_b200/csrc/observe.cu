@@ -77,7 +77,7 @@ observe_kernel(const EnvView v, float *__restrict__ obs, float *__restrict__ vec
         }
         __syncwarp();
         const int nr = (int16_t)(cur.ht.y & 0xffff), nc = (int16_t)((uint32_t)cur.ht.y >> 16);   // human.getNextPos()
-        observe_world<C_T, F_T, VEC4>(v, L, m, lut, w, lane, cur.pw, cur.gw, nr, nc, obs, vec);
+        observe_world<C_T, F_T, VEC4>(v, L, m, lut, w, Grp<32>(lane), cur.pw, cur.gw, nr, nc, obs, vec);
         w = w1;
         cur = nxt;
     }

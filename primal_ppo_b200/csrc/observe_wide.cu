@@ -71,7 +71,7 @@ observe_wide_kernel(const EnvView v, float *__restrict__ obs, float *__restrict_
         // ---- chunks of agents, round-robin over the warps ---------------------------------------------------------------
         for (int k = warp; k < nchunks; k += WIDE_WARPS) {
             const int c0 = k * L.CH;
-            observe_chunk<C_T, F_T, VEC4>(v, L, m, lut, w, lane, c0, min(L.CH, N - c0), nr, nc, rows, cols, obs, vec);
+            observe_chunk<C_T, F_T, VEC4>(v, L, m, lut, w, Grp<32>(lane), c0, min(L.CH, N - c0), nr, nc, rows, cols, obs, vec);
         }
         __syncthreads();
         // ---- un-scatter so that the next world starts from a clean grid ------------------------------------------------

@@ -18,11 +18,12 @@ struct ObsLayout {
     int WB;      // u32 words of the chunk bit string
     int alias;   // 1: the chunk bit string overlays the staging area (single chunk per world)
     int out_bf16; // 0: f32 observations (the reference's layout); 1: the same 0/1 values as bf16 (optional, half the bytes)
-    int step_n, step_e;   // 1024 / PB, 1024 % PB: how (agent, bit) advances when the word index advances by 32
+    int step_n, step_e;   // (32 G) / PB, (32 G) % PB: how (agent, bit) advances when the word index advances by G (the group width)
     size_t off_abits, off_grid, off_goal, off_aw, off_wb, total;
 };
 
-inline ObsLayout make_layout(int HP, int RW, int GS, int N, int C, int F, int CH) {
+// G = lanes that build one world (32 = a whole warp; 8 / 16 = lane groups, several small worlds per warp)
+inline ObsLayout make_layout(int HP, int RW, int GS, int N, int C, int F, int CH, int G = 32) {
     ObsLayout L;
     L.PB = C * F * F;
     int aw = (L.PB + 31) / 32 + 1;
@@ -32,8 +33,8 @@ inline ObsLayout make_layout(int HP, int RW, int GS, int N, int C, int F, int CH
     L.WB = (CH * L.PB + 31) / 32 + 2;
     L.alias = (CH >= N) ? 1 : 0;
     L.out_bf16 = 0;
-    L.step_n = 1024 / L.PB;
-    L.step_e = 1024 % L.PB;
+    L.step_n = (32 * G) / L.PB;
+    L.step_e = (32 * G) % L.PB;
     size_t o = align16((size_t)HP * RW * 4);
     L.off_abits = o; o += align16((size_t)HP * RW * 4);
     L.off_grid = o; o += align16((size_t)HP * GS);
@@ -64,6 +65,7 @@ struct WorldRegs {
     int2 ht;                // human (pos, next) of the current tick
 };
 
+template <int G = 32>
 __device__ __forceinline__ void load_world(const EnvView &v, int w, int lane, int nob, uint64_t pol, WorldRegs &r) {
     if (w < v.W) {
         const size_t base = (size_t)w * v.N;
@@ -72,7 +74,7 @@ __device__ __forceinline__ void load_world(const EnvView &v, int w, int lane, in
         r.gw = ld_keep(reinterpret_cast<const uint32_t *>(v.goal) + base + i, pol);
         const uint32_t *src = v.obst_pack + (size_t)w * v.PW;
 #pragma unroll
-        for (int k = 0; k < OBW; ++k) r.ob[k] = (k * 32 + lane < nob) ? ld_keep(src + k * 32 + lane, pol) : 0u;
+        for (int k = 0; k < OBW; ++k) r.ob[k] = (k * G + lane < nob) ? ld_keep(src + k * G + lane, pol) : 0u;
         r.ht = ld_keep_v2(reinterpret_cast<const int2 *>(v.hcur) + w, pol);
     }
 }
@@ -97,11 +99,12 @@ __device__ __forceinline__ ObsSmem obs_carve(unsigned char *base, const ObsLayou
 // One chunk of agents [c0, c0 + nch) of a staged world by one warp: phase 1 (per-agent bit strings), phase 1b
 // (compaction), phase 2 (bits -> f32, streaming stores).  `aw` / `wb` are this warp's scratch; everything else of `m` is
 // read-only here and may be shared by the warps of a CTA.
-template <int C_T, int F_T, bool VEC4>
+template <int C_T, int F_T, bool VEC4, int G = 32>
 __device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout &L, const ObsSmem &m, const uint4 *lut,
-                                              const int w, const int lane, const int c0, const int nch, const int nr,
+                                              const int w, const Grp<G> &g, const int c0, const int nch, const int nr,
                                               const int nc, const int rows, const int cols, float *__restrict__ obs,
                                               float *__restrict__ vec) {
+    const int lane = g.gl;
     const int N = v.N, P = v.P, GS = v.GS, RW = v.RW;
     const int F = F_T > 0 ? F_T : v.F, C = C_T > 0 ? C_T : v.C, half = F >> 1;
     const int FF = F * F, PB = (C_T > 0 && F_T > 0) ? C_T * F_T * F_T : L.PB, AST = L.AST;
@@ -200,13 +203,13 @@ __device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout 
             o4.w = 0.0f;
             reinterpret_cast<float4 *>(vec)[(size_t)w * N + i] = o4;
         }
-        __syncwarp();
+        g.sync();
         // ---- phase 1b: compact to one contiguous bit string (word m <- 32 bits starting at agent n, bit e) --------
         const int TB = nch * PB;
         const int nwords = (TB + 31) >> 5;
         {
             int n = (lane << 5) / PB, e = (lane << 5) - n * PB;
-            for (int m = lane; m < nwords; m += 32) {
+            for (int m = lane; m < nwords; m += G) {
                 const uint32_t *src = aw + n * AST;
                 uint32_t x = __funnelshift_r(src[e >> 5], src[(e >> 5) + 1], e & 31);
                 const int valid = PB - e;
@@ -219,14 +222,14 @@ __device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout 
                 if (e >= PB) { e -= PB; n += 1; }
             }
         }
-        __syncwarp();
+        g.sync();
         // ---- phase 2: bits -> floats, streaming stores ---------------------------------------------------------
         if (L.out_bf16) {
             // optional bf16 output: 8 bits -> 8 bf16 (1.0 = 0x3F80) -> one 16-byte store; the expansion is plain ALU
             uint16_t *dst16 = reinterpret_cast<uint16_t *>(obs) + ((size_t)w * N + c0) * PB;
             if (VEC4) {
                 const int n8 = TB >> 3;
-                for (int q = lane; q < n8; q += 32) {
+                for (int q = lane; q < n8; q += G) {
                     const uint32_t b = wb[q >> 2] >> ((q & 3) << 3);
                     const uint32_t x0 = (b & 1u) * 0x3F80u | (b & 2u) * 0x1FC00000u;
                     const uint32_t x1 = ((b >> 2) & 1u) * 0x3F80u | ((b >> 2) & 2u) * 0x1FC00000u;
@@ -234,11 +237,11 @@ __device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout 
                     const uint32_t x3 = ((b >> 6) & 1u) * 0x3F80u | ((b >> 6) & 2u) * 0x1FC00000u;
                     st_stream_v4(reinterpret_cast<float *>(dst16 + ((size_t)q << 3)), x0, x1, x2, x3);
                 }
-                for (int f = (n8 << 3) + lane; f < TB; f += 32) dst16[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 0x3F80 : 0;
+                for (int f = (n8 << 3) + lane; f < TB; f += G) dst16[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 0x3F80 : 0;
             } else {
-                for (int f = lane; f < TB; f += 32) dst16[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 0x3F80 : 0;
+                for (int f = lane; f < TB; f += G) dst16[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 0x3F80 : 0;
             }
-            __syncwarp();
+            g.sync();
             return;
         }
         float *dst = obs + ((size_t)w * N + c0) * PB;
@@ -248,14 +251,14 @@ __device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout 
             const uint32_t *wp = wb + (lane >> 3);
             float *d4 = dst + (lane << 2);
 #pragma unroll 4
-            for (int q = lane; q < n4; q += 32, wp += 4, d4 += 128) {
+            for (int q = lane; q < n4; q += G, wp += G / 8, d4 += 4 * G) {
                 const uint4 val = lut[(*wp >> sh) & 15u];
                 st_stream_v4(d4, val.x, val.y, val.z, val.w);
             }
         } else {
-            for (int f = lane; f < TB; f += 32) dst[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 1.0f : 0.0f;
+            for (int f = lane; f < TB; f += G) dst[f] = ((wb[f >> 5] >> (f & 31)) & 1u) ? 1.0f : 0.0f;
         }
-        __syncwarp();
+        g.sync();
     }
 }
 
@@ -263,41 +266,42 @@ __device__ __forceinline__ void observe_chunk(const EnvView &v, const ObsLayout 
 // from HBM); (nr, nc) = human.getNextPos(); the obstacle bit rows are already staged in m.obits and m.abits / m.grid
 // are clean on entry.  On exit they are clean again unless L.alias (then the caller re-zeroes them for the next world).
 // C_T/F_T > 0: compile-time channels / FOV (the training configuration 6 x 9 x 9); 0: runtime values from EnvView.
-template <int C_T, int F_T, bool VEC4>
+template <int C_T, int F_T, bool VEC4, int G = 32>
 __device__ __forceinline__ void observe_world(const EnvView &v, const ObsLayout &L, const ObsSmem &m, const uint4 *lut,
-                                              const int w, const int lane, const uint32_t pw_reg, const uint32_t gw_reg,
+                                              const int w, const Grp<G> &g, const uint32_t pw_reg, const uint32_t gw_reg,
                                               const int nr, const int nc, float *__restrict__ obs,
                                               float *__restrict__ vec) {
+    const int lane = g.gl;
     const int N = v.N, P = v.P, GS = v.GS, RW = v.RW, CH = L.CH;
     uint32_t *const abits = m.abits, *const sgoal = m.sgoal, *const spos = m.spos;
     uint8_t *const grid = m.grid;
     {
         const uint32_t *posw = reinterpret_cast<const uint32_t *>(v.pos) + (size_t)w * N;
         const uint32_t *goalw = reinterpret_cast<const uint32_t *>(v.goal) + (size_t)w * N;
-        for (int i = lane; i < N; i += 32) {
-            const uint32_t pw = i < 32 ? pw_reg : __ldg(posw + i);
+        for (int i = lane; i < N; i += G) {
+            const uint32_t pw = i < G ? pw_reg : __ldg(posw + i);
             const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
             grid[(r + P) * GS + c + P] = (uint8_t)(i + 1);
             atomicOr(&abits[(r + P) * RW + ((c + P) >> 5)], 1u << ((c + P) & 31));
-            sgoal[i] = i < 32 ? gw_reg : __ldg(goalw + i);
+            sgoal[i] = i < G ? gw_reg : __ldg(goalw + i);
             spos[i] = pw;
         }
         int rows = v.H, cols = v.Wd;
         if (v.use_da | v.use_hp) { if (v.dims) { rows = v.dims[2 * w]; cols = v.dims[2 * w + 1]; } }
-        __syncwarp();
+        g.sync();
 
         for (int c0 = 0; c0 < N; c0 += CH)
-            observe_chunk<C_T, F_T, VEC4>(v, L, m, lut, w, lane, c0, min(CH, N - c0), nr, nc, rows, cols, obs, vec);
+            observe_chunk<C_T, F_T, VEC4, G>(v, L, m, lut, w, g, c0, min(CH, N - c0), nr, nc, rows, cols, obs, vec);
         if (!L.alias) {
             // un-scatter this world's agents so the next world starts from a clean grid
-            for (int i = lane; i < N; i += 32) {
+            for (int i = lane; i < N; i += G) {
                 const uint32_t pw = spos[i];
                 const int r = (int16_t)(pw & 0xffff), c = (int16_t)(pw >> 16);
                 grid[(r + P) * GS + c + P] = 0;
                 abits[(r + P) * RW + ((c + P) >> 5)] = 0;
             }
         }
-        __syncwarp();
+        g.sync();
     }
 }
 

@@ -59,7 +59,7 @@ step_kernel(const EnvView v, const int8_t *__restrict__ actions, const int8_t *_
             for (int k = lane; k < npw; k += 32) s.obits[k] = __ldg(src + k);
         }
         uint32_t new_pw, new_gw;
-        resolve_world<MODE, true>(v, out, s, w, lane, cur, pol, new_pw, new_gw);
+        resolve_world<MODE, true>(v, out, s, w, Grp<32>(lane), cur, pol, new_pw, new_gw);
         __syncwarp();
         w = w1;
         cur = nxt;

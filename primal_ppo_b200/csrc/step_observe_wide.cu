@@ -82,7 +82,7 @@ step_observe_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, co
         // ---- phase B: chunks of agents, round-robin over the warps -----------------------------------------------------------
         for (int k = warp; k < nchunks; k += FW_WARPS) {
             const int c0 = k * L.CH;
-            observe_chunk<C_T, F_T, VEC4>(v, L, m, lut, w, lane, c0, min(L.CH, N - c0), nr, nc, rows, cols, obs, vec);
+            observe_chunk<C_T, F_T, VEC4>(v, L, m, lut, w, Grp<32>(lane), c0, min(L.CH, N - c0), nr, nc, rows, cols, obs, vec);
         }
         __syncthreads();
         for (int i = tid; i < N; i += blockDim.x) {        // un-scatter: the next world starts from a clean grid

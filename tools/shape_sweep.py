@@ -15,8 +15,8 @@ build()
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 peak, _ = bench.measured_peaks()
-for (W, H, N, F) in ((65536, 40, 33, 9), (32768, 40, 48, 9), (16384, 60, 100, 9), (16384, 80, 64, 9), (16384, 80, 128, 9), (8192, 128, 128, 9), (8192, 80, 100, 15),
-                     (4096, 80, 40, 31)):
+for (W, H, N, F) in ((4096, 20, 8, 9), (65536, 20, 8, 9), (262144, 10, 8, 9), (131072, 20, 16, 9), (262144, 20, 2, 9), (131072, 40, 4, 9), (65536, 40, 12, 9),
+                     (65536, 40, 32, 9)):
     dsc = generate_scenario_device(W, H, H, N, kind="density", density=(0.0, 0.3), queue_len=4, seed=3, device=dev, fov=F)
     env = BatchedMapfGym(dsc, device=dev, use_tape=False)
     obs = torch.empty((W, N, 6, F, F), device=dev); vec = torch.empty((W, N, 4), device=dev)
