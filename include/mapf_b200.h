@@ -43,7 +43,9 @@ extern "C" {
 #define MAPF_E_UNSUPPORTED (-4)
 #define MAPF_E_STATE (-5)
 
-/* per-world error bits (err[w]); the reference raises or hangs in these situations */
+/* per-world error bits (err[w]); the reference raises or hangs in these situations.  For NO_VIABLE and FIX_ITER_CAP every agent
+ * of the world stays in that step (whatever fixActions had committed so far need not be collision-free), so a flagged world
+ * remains a valid state and keeps stepping. */
 #define MAPF_ERR_NO_VIABLE 1u    /* IndexError from random.choice([])        mapf_gym.py:588 */
 #define MAPF_ERR_FIX_ITER_CAP 2u /* livelock of the fixActions while loop     mapf_gym.py:563 */
 #define MAPF_ERR_BAD_ACTION 4u   /* action outside 0..4                       mapf_gym.py:452-456 */

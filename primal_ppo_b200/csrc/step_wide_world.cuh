@@ -217,7 +217,12 @@ __device__ __forceinline__ void step_wide_world(const EnvView &v, const int8_t *
         if (tid == 0) {
             int head = 0, tail = 0, iters = 0;
             uint32_t draw = 0;
-            for (int i = 0; i < N; ++i) if (s.st[i] < 0 && !s.good[i]) s.queue[(tail++) & 255] = (uint8_t)i;
+            // problem agents that own a good action committed above; the reference's loop spends one iteration on each of
+            // them before any re-queued agent, so they count towards the iteration cap (see step_world.cuh)
+            for (int i = 0; i < N; ++i) {
+                if (s.st[i] < 0 && !s.good[i]) s.queue[(tail++) & 255] = (uint8_t)i;
+                else if (s.st[i] < 0) iters++;
+            }
             while (head < tail) {
                 if (++iters > FIX_CAP) { errbits |= MAPF_ERR_FIX_ITER_CAP; break; }
                 const int k = s.queue[(head++) & 255];
@@ -271,6 +276,8 @@ __device__ __forceinline__ void step_wide_world(const EnvView &v, const int8_t *
                 }
                 s.commit[k] = (int8_t)choice;
             }
+            // livelock cap / no viable action: every agent of the world stays in this step (see step_world.cuh)
+            if (errbits & (MAPF_ERR_FIX_ITER_CAP | MAPF_ERR_NO_VIABLE)) for (int i = 0; i < N; ++i) s.commit[i] = 0;
         }
     } else {
         for (int i = tid; i < N; i += nthreads) s.commit[i] = s.act[i];

@@ -232,7 +232,11 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
         const uint32_t qm = g.ballot(inq);
         if (qm) {
             if (inq) s.queue[__popc(qm & ((1u << lane) - 1u))] = (int8_t)lane;
-            int head = 0, tail = __popc(qm), iters = 0;
+            // The reference's loop pops EVERY problem agent, also those that own a good action (one iteration each, :568-571);
+            // here they committed above without being queued.  They all precede the first re-queued agent, so counting them
+            // up front makes the iteration cap fall on the same pop as in the oracle (a capped world then keeps evolving
+            // identically on both sides; the cap itself cannot fall among the <= N initial entries).
+            int head = 0, tail = __popc(qm), iters = __popc(g.ballot(problem && good != 0));
             uint32_t draw = 0;
             g.sync();
             // Every iteration is executed by the whole warp on warp-uniform values: the popped agent's masks arrive by
@@ -347,6 +351,10 @@ __device__ __forceinline__ void resolve_world(const EnvView &v, const MapfStepOu
         }
         g.sync();
         if (active) { f = s.commit[lane]; if (f < 0) f = 0; }
+        // The reference hangs (livelock) or raises (IndexError) here; whatever the loop had committed so far need not be
+        // collision-free (an agent left at -1 stays where another may already be headed).  Every agent of such a world
+        // stays in this step: nobody moves, so the world remains a valid state and keeps stepping identically in the oracle.
+        if (errbits & (MAPF_ERR_FIX_ITER_CAP | MAPF_ERR_NO_VIABLE)) f = 0;
     }
 
     // ---- moves, goal arrival, human tick, constraint violations (:620-633) ----------------------------------

@@ -429,3 +429,39 @@ def test_gpu_env_on_another_device_than_the_current_one():
     from primal_ppo_b200 import decode_results
     _eq(decode_results(ring["slots"][0]["packed"])["reward"].numpy(), _np(o0.reward), "host call on cuda:1")
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("shape", [(513, 6, 5, 9, True), (513, 13, 7, 29, True), (200, 8, 8, 20, False), (64, 9, 9, 40, True)])
+def test_gpu_flagged_worlds_stay_valid_and_identical(shape):
+    """Worlds on which the reference would hang (fixActions livelock) or raise (no viable action, no free cell) are flagged,
+    every agent stays for that step, and the world keeps stepping: state, outputs and later flags of such worlds equal the
+    oracle's for every world and every step — nothing is excluded from the comparison.  (Found by tools/soak_parity.py: before
+    the iteration cap counted the reference's pops of agents that own a good action, and before a capped step froze the
+    world, flagged worlds drifted apart.)"""
+    W, H, Wd, N, gs = shape
+    sc = random_scenario(W, H, Wd, N, density=(0.0, 0.35), queue_len=1 if gs else 3, seed=809596303 % (1 << 30), fov=9, unique_maps=24)
+    env = _env(sc, use_tape=False, seed=5, goal_sampling=gs)
+    orc = OracleMapfGym(sc, seed=5, threads=8, use_tape=False, goal_sampling=gs)
+    acts = random_actions(30, W, N, seed=6)
+    flagged_steps = 0
+    for t in range(30):
+        ref = orc.step(acts[t])
+        if t % 2:
+            out, obs, vec = env.step_observe(torch.from_numpy(acts[t]))
+        else:
+            out = env.step(torch.from_numpy(acts[t])); obs, vec = env.getAllObservations()
+        so, s = orc.state(), env.state()
+        _eq(_np(s["err"]).astype(np.uint32), so["err"], f"t={t} err flags")
+        for k in ("status", "reward", "cost", "train_valid", "goals_reached", "violated"):
+            _eq(_np(getattr(out, k)), ref[k], f"t={t} {k}")
+        _eq(_np(out.fixed_actions), ref["fixed"], f"t={t} fixed")
+        for k in ("pos", "goal", "rep"):
+            _eq(_np(s[k]), so[k], f"t={t} {k}")
+        o_obs, o_vec = orc.getAllObservations()
+        assert torch.equal(obs, torch.from_numpy(o_obs).cuda()) and torch.equal(vec, torch.from_numpy(o_vec).cuda()), f"t={t} obs"
+        flagged_steps += int((so["err"] != 0).sum())
+        # a world stays a valid state: no two agents share a cell
+        p = so["pos"].astype(np.int64)
+        cell = p[..., 0] * Wd + p[..., 1]
+        assert all(len(set(row)) == N for row in cell.tolist()), f"t={t}: two agents on one cell"
+    assert flagged_steps > 0, "the scenario was meant to produce flagged worlds"
