@@ -78,3 +78,29 @@ def test_bfs_maps_are_distance_fields(seed, shape, dens):
             nmin = np.minimum.reduce([pad[:-2, 1:-1], pad[2:, 1:-1], pad[1:-1, :-2], pad[1:-1, 2:]])
             inner = reach & (m > 0)
             assert (nmin[inner] == m[inner] - 1).all()
+
+
+def test_oracle_flagged_worlds_stay_valid():
+    """Worlds on which the reference would hang (fixActions livelock, mapf_gym.py:563) or raise (IndexError, :588) are flagged and
+    every agent stays for that step: whatever the step, no two agents ever share a cell and nobody stands on an obstacle."""
+    import numpy as np
+    from oracle import OracleMapfGym
+    from primal_ppo_b200 import random_actions, random_scenario
+    W, H, Wd, N = 300, 6, 5, 9
+    sc = random_scenario(W, H, Wd, N, density=(0.0, 0.35), queue_len=2, seed=12, unique_maps=24)
+    orc = OracleMapfGym(sc, seed=3, threads=4, use_tape=False)
+    acts = random_actions(40, W, N, seed=4)
+    for t in range(40):
+        before = orc.state()["pos"].copy()
+        e0 = orc.state()["err"].copy()
+        out = orc.step(acts[t])
+        s = orc.state()
+        p = s["pos"].astype(np.int64)
+        cell = p[..., 0] * Wd + p[..., 1]
+        assert all(len(set(r)) == N for r in cell.tolist()), f"t={t}: two agents on one cell"
+        assert (sc.obst[np.arange(W)[:, None], p[..., 0], p[..., 1]] == 0).all()
+        newly = (s["err"] & 3) & ~(e0 & 3)                       # NO_VIABLE / FIX_ITER_CAP raised in THIS step
+        if newly.any():
+            np.testing.assert_array_equal(s["pos"][newly != 0], before[newly != 0])     # nobody moved in such a world
+            assert (out["fixed"][newly != 0] == 0).all()
+    assert (orc.state()["err"] & 3).any(), "the scenario was meant to produce flagged worlds"
