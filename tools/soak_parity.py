@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Randomised differential soak: random shapes (grid, agents, FOV, channels, density, goal sampling on/off, eval channels), the
-CUDA path (fused launch, two launches, five-call API in rotation) against the oracle on every output of every step, for EVERY
+CUDA path (fused launch or the split-phase host call with the compact slab, two launches, five-call API in rotation; BFS maps
+refreshed in place after every step) against the oracle on every output of every step, for EVERY
 world — also those carrying error flags (where the reference would have hung or raised, every agent stays for that step).
 SOAK_CROWDED=1 draws small dense worlds (fixActions queues, evictions, livelock caps, no-free-cell flags).
     python tools/soak_parity.py [seconds] [seed]
@@ -50,11 +51,25 @@ while time.time() < t_end:
     env = BatchedMapfGym(sc, use_tape=False, seed=seed, goal_sampling=gs)
     orc = OracleMapfGym(sc, seed=seed, threads=8, use_tape=False, goal_sampling=gs)
     acts = random_actions(T, W, N, seed=seed + 1)
+    maps = env.bfs_maps() if rng.random() < 0.5 else None          # kept current with mapf_bfs_refresh after every step
+    use_host = rng.random() < 0.3                                   # the split-phase host call (compact slab) instead of mode 0
+    ring = env.make_host_ring(slots=2, action_slots=2, compact=True, numa_bind=False) if use_host else None
+    obs_h = torch.empty((W, N, C, F, F), device="cuda") if use_host else None
+    vec_h = torch.empty((W, N, 4), device="cuda") if use_host else None
     for t in range(T):
         a = torch.from_numpy(acts[t])
         mode = (t + n_scen) % 3
         ref = orc.step(acts[t])
-        if mode == 0:
+        if mode == 0 and use_host:
+            from primal_ppo_b200 import decode_results
+            ring["action_ring"][t & 1].copy_(a)
+            env.step_observe_host_begin(ring["action_ring"][t & 1], ring["slots"][t & 1], obs_h, vec_h, train_valid_dev=env._out.train_valid)
+            env.host_wait(0)
+            dec = decode_results(ring["slots"][t & 1]["packed"])
+            out = type("O", (), dict(status=dec["status"], reward=dec["reward"], cost=dec["cost"], train_valid=env._out.train_valid,
+                                     goals_reached=dec["goals_reached"], violated=dec["violated"]))
+            obs, vec = obs_h, vec_h
+        elif mode == 0:
             out, obs, vec = env.step_observe(a)
         elif mode == 1:
             out = env.step(a); obs, vec = env.getAllObservations()
@@ -82,11 +97,15 @@ while time.time() < t_end:
         o_obs, o_vec = orc.getAllObservations()
         if obs.cpu().numpy()[ok].tobytes() != o_obs[ok].tobytes() or vec.cpu().numpy()[ok].tobytes() != o_vec[ok].tobytes():
             print("MISMATCH obs/vec", dict(W=W, H=H, Wd=Wd, N=N, F=F, C=C, gs=gs, ev=ev, seed=seed, t=t, mode=mode)); sys.exit(1)
+        if maps is not None:
+            env.refresh_bfs(maps, torch.from_numpy(ref["goals_reached"]).cuda())
         n_steps += 1
         n_agent_steps += int(ok.sum()) * N
-    if (H * Wd) % 8 == 0 or True:
-        if env.bfs_maps().cpu().numpy()[ok].tobytes() != orc.bfs_maps()[ok].tobytes():
-            print("MISMATCH bfs", dict(W=W, H=H, Wd=Wd, N=N, F=F, seed=seed)); sys.exit(1)
+    ob = orc.bfs_maps()
+    if env.bfs_maps().cpu().numpy().tobytes() != ob.tobytes():
+        print("MISMATCH bfs", dict(W=W, H=H, Wd=Wd, N=N, F=F, seed=seed)); sys.exit(1)
+    if maps is not None and maps.cpu().numpy().tobytes() != ob.tobytes():
+        print("MISMATCH bfs maps refreshed in place", dict(W=W, H=H, Wd=Wd, N=N, F=F, seed=seed, gs=gs)); sys.exit(1)
     n_scen += 1
     print(f"ok  W={W:4d} {H:3d}x{Wd:<3d} N={N:3d} F={F:2d} C={C} goal_sampling={int(gs)} eval={int(ev)} T={T} flagged={int(flagged.sum())}", flush=True)
     del env, orc
