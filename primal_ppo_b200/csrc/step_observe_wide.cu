@@ -157,20 +157,26 @@ bool step_observe_wide_fusable(const EnvView &v) {
 
 cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, const MapfStepOut &out, float *obs, float *vec,
                                      int *work_counter, cudaStream_t stream, int out_bf16) {
-    // variant: MAPF_DBG_FLAGS bits 24-25 (experiments): 0 = default, 1 = 8 warps x 3 CTAs, 2 = 4 warps x 6, 3 = 4 warps x 8
     // Default: 4-warp CTAs when six of them fit an SM (measured on 80x80x128, ms per step for FOV 9 / 15 / 21 / 31:
     // two launches 0.861 / 0.971 / 0.950 / 1.032; 8 warps x 3: 1.033 / 1.018 / 0.887 / 1.027; 4 warps x 6: 0.701 / 0.898 /
     // 0.870 / 1.077 — at FOV 31 the per-warp observation scratch leaves three 4-warp CTAs, too few warps for the stores).
-    int variant = (v.dbg_flags >> 24) & 3;
+    int variant = (v.dbg_flags >> 24) & 7;                  // experiments: 1 = 8w x 3, 2 = 4w x 6, 3 = 4w x 8, 4 = 2w x 16
     if (variant == 0) {
         const WidePlan p4 = make_plan(v, out_bf16, 4);
         // ... and eight of them (compiled for 64 registers) when eight fit: mid-size worlds (33..100 agents) have a short
         // store phase per world, so they need even more worlds in flight (40x40x64: 0.771 vs 0.806 ms; 80x80x64: 0.384 vs 0.406)
         variant = !(p4.ok && p4.smem <= 40 * 1024) ? 1 : (p4.smem <= 28 * 1024 ? 3 : 2);
+        // ... and up to 64 agents, 2-warp CTAs x 16: 33..64-agent worlds have the shortest store phase of all (64-124 KB) against
+        // the same ~20 us step phase (40x40x33: 0.927 vs 1.139 ms; 40x40x48: 0.574 vs 0.680; 24x24x40: 0.609 vs 0.750)
+        if (v.N <= 64) {
+            const WidePlan p2 = make_plan(v, out_bf16, 2);
+            if (p2.ok && p2.smem <= 24 * 1024) variant = 4;
+        }
     }
-    const int warps = variant == 1 ? 8 : 4;
+    if (variant == 4 && v.N > 64) variant = 3;
+    const int warps = variant == 1 ? 8 : (variant == 4 ? 2 : 4);
     WidePlan p = make_plan(v, out_bf16, warps);
-    if (!p.ok && warps == 4) { variant = 1; p = make_plan(v, out_bf16, 8); }
+    if (!p.ok && warps != 8) { variant = 1; p = make_plan(v, out_bf16, 8); }
     if (!p.ok) return cudaErrorNotSupported;
     const int PB = v.C * v.F * v.F;
     const size_t al = out_bf16 ? 8 : 4;
@@ -194,6 +200,7 @@ cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, co
     do {                                                                                                           \
         if (variant == 1) LAUNCH(8, 3, __VA_ARGS__);                                                               \
         else if (variant == 2) LAUNCH(4, 6, __VA_ARGS__);                                                          \
+        else if (variant == 4) LAUNCH(2, 16, __VA_ARGS__);                                                         \
         else LAUNCH(4, 8, __VA_ARGS__);                                                                            \
     } while (0)
     if (v.C == 6 && v.F == 9) { if (vec4) LAUNCH_V(6, 9, true); else LAUNCH_V(6, 9, false); }
