@@ -173,7 +173,6 @@ cudaError_t launch_step_observe_wide(const EnvView &v, const int8_t *actions, co
             if (p2.ok && p2.smem <= 24 * 1024) variant = 4;
         }
     }
-    if (variant == 4 && v.N > 64) variant = 3;
     const int warps = variant == 1 ? 8 : (variant == 4 ? 2 : 4);
     WidePlan p = make_plan(v, out_bf16, warps);
     if (!p.ok && warps != 8) { variant = 1; p = make_plan(v, out_bf16, 8); }

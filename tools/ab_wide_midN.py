@@ -13,7 +13,7 @@ from primal_ppo_b200.build import build  # noqa: E402
 build()
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
-for (W, H, N, F) in ((65536, 40, 33, 9), (32768, 40, 48, 9), (32768, 40, 64, 9), (16384, 80, 64, 9), (32768, 24, 40, 9), (16384, 40, 64, 15)):
+for (W, H, N, F) in ((16384, 80, 128, 9), (16384, 60, 100, 9), (8192, 128, 128, 9), (8192, 80, 128, 15), (4096, 80, 128, 21)):
     dsc = generate_scenario_device(W, H, H, N, kind="density", density=(0.0, 0.3), queue_len=4, seed=3, device=dev, fov=F)
     obs = torch.empty((W, N, 6, F, F), device=dev); vec = torch.empty((W, N, 4), device=dev)
     gen = torch.Generator(device=dev); gen.manual_seed(1)
