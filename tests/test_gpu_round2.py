@@ -95,7 +95,7 @@ def test_gpu_full_size_65536x40x40x32_fused_steps_match_oracle():
             so = orc.state()
             g = rec[t + 1]
             np.testing.assert_array_equal(g["err"][lo:hi], so["err"], err_msg=f"t={t} err flags {lo}")
-            ok = so["err"] == 0                         # worlds on which the reference would have raised are excluded
+            ok = np.ones_like(so["err"], dtype=bool)    # flagged worlds (the reference would have hung / raised) are compared too
             for k, ok_ in (("status", "status"), ("reward", "reward"), ("cost", "cost"), ("train_valid", "train_valid"),
                            ("goals_reached", "goals_reached"), ("violated", "violated"), ("shadow_goals", "shadow"),
                            ("fixed_actions", "fixed")):
@@ -108,7 +108,7 @@ def test_gpu_full_size_65536x40x40x32_fused_steps_match_oracle():
         n_flagged += int((orc.state()["err"] != 0).sum())
         if lo == 0:
             m = orc.bfs_maps()[:4096].reshape(4096 * N, -1)
-            okb = np.repeat(orc.state()["err"][:4096] == 0, N)
+            okb = np.ones(4096 * N, dtype=bool)
             np.testing.assert_array_equal(bfs_sum.view(np.uint64)[okb], orc_checksum_rows(m, threads)[okb])
         del orc
     assert n_flagged < W // 100
@@ -224,7 +224,7 @@ def test_gpu_goal_sampling_on_device_matches_oracle(shape):
             obs, vec = env.getAllObservations()
         so, s = orc.state(), env.state()
         np.testing.assert_array_equal(_np(s["err"]).astype(np.uint32), so["err"], err_msg=f"t={t} err")
-        ok = so["err"] == 0
+        ok = np.ones_like(so["err"], dtype=bool)
         for key in ("status", "reward", "goals_reached", "violated"):
             _eq(_np(getattr(out, key))[ok], ref[key][ok], f"t={t} {key}")
         _eq(_np(s["pos"])[ok], so["pos"][ok], f"t={t} pos")
