@@ -228,9 +228,9 @@ __device__ __forceinline__ void finish_work(int *counter, int total_warps, int l
 // per-world register loads that follow a few microseconds later then hit L2.
 constexpr int PFB = 256;
 __device__ __forceinline__ int prefetch_batch(const EnvView &v) { return PFB << ((v.dbg_flags >> 8) & 7); }
-__device__ __forceinline__ void prefetch_world_batch(const EnvView &v, const int8_t *actions, int w0, uint64_t pol) {
+__device__ __forceinline__ void prefetch_world_batch(const EnvView &v, const int8_t *actions, int w0, uint64_t pol, int batch = 0) {
     if (w0 >= v.W) return;
-    const size_t n = (size_t)min(prefetch_batch(v), v.W - w0), wn = (size_t)w0 * v.N, nn = n * v.N;
+    const size_t n = (size_t)min(batch > 0 ? batch : prefetch_batch(v), v.W - w0), wn = (size_t)w0 * v.N, nn = n * v.N;
     prefetch_l2_bulk(v.obst_pack + (size_t)w0 * v.PW, n * v.PW * 4, pol);
     prefetch_l2_bulk(reinterpret_cast<const uint32_t *>(v.pos) + wn, nn * 4, pol);
     prefetch_l2_bulk(reinterpret_cast<const uint32_t *>(v.goal) + wn, nn * 4, pol);

@@ -56,12 +56,17 @@ step_observe_wide_kernel(const EnvView v, const int8_t *__restrict__ actions, co
     for (int k = tid; k < nob; k += blockDim.x) m.abits[k] = 0;
     for (int k = tid; k < (HP * GS) / 16; k += blockDim.x) reinterpret_cast<uint4 *>(m.grid)[k] = make_uint4(0, 0, 0, 0);
     const int nchunks = (N + L.CH - 1) / L.CH;
+    const uint64_t pol = policy_evict_last();
+    // prefetch distance: worlds here are 2..8 times larger than in the warp-per-world kernel, so fewer of them make a batch
+    const int pf_batch = 64, pf_ahead = (v.dbg_flags & (1 << 29)) ? -1 : 128;
     for (;;) {
         __syncthreads();                                   // previous world fully written, grid / abits clean
         if (tid == 0) s_world = atomicAdd(work_counter, 1);
         __syncthreads();
         const int w = s_world;
         if (w >= v.W) break;
+        // batched L2 prefetch of the state a few hundred worlds ahead (worlds are claimed in increasing order; common.cuh)
+        if (tid == 0 && pf_ahead >= 0 && (w & (pf_batch - 1)) == 0) prefetch_world_batch(v, actions, w + pf_ahead, pol, pf_batch);
         expand_obstacle_rows(m.obits, v.obst_pack + (size_t)w * v.PW, v, tid, blockDim.x);
         int rows = v.H, cols = v.Wd;
         if (v.use_da | v.use_hp) { if (v.dims) { rows = v.dims[2 * w]; cols = v.dims[2 * w + 1]; } }
