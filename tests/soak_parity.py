@@ -4,7 +4,7 @@ CUDA path (fused launch or the split-phase host call with the compact slab, two 
 refreshed in place after every step) against the oracle on every output of every step, for EVERY
 world — also those carrying error flags (where the reference would have hung or raised, every agent stays for that step).
 SOAK_CROWDED=1 draws small dense worlds (fixActions queues, evictions, livelock caps, no-free-cell flags).
-    python tools/soak_parity.py [seconds] [seed]
+    python tests/soak_parity.py [seconds] [seed]        (a script, not collected by pytest; it lives under tests/ because it drives the oracle)
 Prints one line per scenario and a summary; exits non-zero on the first mismatch."""
 import os
 import sys
@@ -13,7 +13,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 from oracle import OracleMapfGym  # noqa: E402
 from primal_ppo_b200 import BatchedMapfGym, random_actions, random_scenario  # noqa: E402
 from primal_ppo_b200.build import build  # noqa: E402

@@ -435,7 +435,7 @@ def test_gpu_env_on_another_device_than_the_current_one():
 def test_gpu_flagged_worlds_stay_valid_and_identical(shape):
     """Worlds on which the reference would hang (fixActions livelock) or raise (no viable action, no free cell) are flagged,
     every agent stays for that step, and the world keeps stepping: state, outputs and later flags of such worlds equal the
-    oracle's for every world and every step — nothing is excluded from the comparison.  (Found by tools/soak_parity.py: before
+    oracle's for every world and every step — nothing is excluded from the comparison.  (Found by tests/soak_parity.py: before
     the iteration cap counted the reference's pops of agents that own a good action, and before a capped step froze the
     world, flagged worlds drifted apart.)"""
     W, H, Wd, N, gs = shape
