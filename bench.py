@@ -38,6 +38,11 @@ N_AGENTS = 32
 FOV, CH = 9, 6
 
 
+def bench_config(worlds_per_gpu):
+    """The `config` object of BOTH arms (the GPU arm and `--impl reference`): the workload BASELINE.json's metric is quoted on."""
+    return {"workload": WORKLOAD, "worlds_per_gpu": worlds_per_gpu, "agents": N_AGENTS, "grid": [H, WD], "fov": FOV, "channels": CH}
+
+
 def algorithmic_bytes(n_agents=N_AGENTS, h=H, wd=WD, c=CH, f=FOV):
     """SURVEY.md §8d, per agent-step: step ~ 46 + (H*Wd+8)/N, observe ~ 16 + 4*C*F^2 + (H*Wd+8)/N + 8, and for the
     fused step+observe launch B = 62 + 4*C*F^2 + (H*Wd+8)/N (the world's map and human are read once)."""
@@ -442,7 +447,8 @@ def run_reference(args):
             "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/i16 state, f32 obs", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU path on a bounded sample of the same workload"},
+            "config": bench_config(args.worlds),
+            "notes": {"sample": "the CPU path is timed on a bounded sample of the workload: " + sample},
             "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "C/OpenMP restatement of mapf_gym.py (oracle/mapf_oracle.c), pinned bit-exact to the "
                                      "reference; the unmodified Python reference on the same cores is under python_reference"},
@@ -796,11 +802,11 @@ def main():
         line = {"metric": "agent-steps/sec step+observe (40x40, 32 agents)", "value": value, "unit": "agent-steps/s",
                 "n_gpus": world_size, "steps": K, "warmup": Wu, "ms_per_step": total_ms_max / K, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16 state, f32 obs", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "worlds_per_gpu": Wn, "agents": N, "grid": [H, WD], "fov": FOV,
-                           "channels": CH, "actions": "uniform random, device-resident ring of 8",
-                           "call": "mapf_step_observe (one fused launch per step)",
-                           "l2": "working set per step (obs 4.08 GB/GPU written) far exceeds the 126 MB L2; no flush needed",
-                           "worlds_with_error_flags": err_frac},
+                "config": bench_config(Wn),
+                "notes": {"actions": "uniform random, device-resident ring of 8",
+                          "call": "mapf_step_observe (one fused launch per step)",
+                          "l2": "working set per step (obs 4.08 GB/GPU written) far exceeds the 126 MB L2; no flush needed",
+                          "worlds_with_error_flags": err_frac},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": Ke, "note": "mapf_step_observe_host_begin/_wait (split-phase, compact wire format): every step the joint "
