@@ -48,8 +48,13 @@ while time.time() < t_end:
                              use_da=ev, use_hp=ev and C == 6, unique_maps=min(W, 24))
     except Exception as ex:                                   # a shape the host-side generator cannot place
         continue
-    env = BatchedMapfGym(sc, use_tape=False, seed=seed, goal_sampling=gs)
-    orc = OracleMapfGym(sc, seed=seed, threads=8, use_tape=False, goal_sampling=gs)
+    off = 0
+    if W > 8 and rng.random() < 0.3:                            # a shard of a larger job: worlds [lo, hi) with world_offset = lo
+        lo = int(rng.integers(1, W // 2)); hi = int(rng.integers(lo + 1, W + 1))
+        sc = sc.slice(lo, hi); off = lo; W = hi - lo
+    env = BatchedMapfGym(sc, use_tape=False, seed=seed, goal_sampling=gs, world_offset=off)
+    orc = OracleMapfGym(sc, seed=seed, threads=8, use_tape=False, goal_sampling=gs, world_offset=off)
+    ckpt_at = int(rng.integers(0, T)) if rng.random() < 0.25 else -1     # save_state / load_state round trip in the middle
     acts = random_actions(T, W, N, seed=seed + 1)
     maps = env.bfs_maps() if rng.random() < 0.5 else None          # kept current with mapf_bfs_refresh after every step
     use_host = rng.random() < 0.3                                   # the split-phase host call (compact slab) instead of mode 0
@@ -57,6 +62,10 @@ while time.time() < t_end:
     obs_h = torch.empty((W, N, C, F, F), device="cuda") if use_host else None
     vec_h = torch.empty((W, N, 4), device="cuda") if use_host else None
     for t in range(T):
+        if t == ckpt_at:                                            # checkpoint, scramble, restore: the rollout must continue unchanged
+            blob = env.save_state().clone()
+            env.step(torch.from_numpy(acts[(t + 1) % T]))
+            env.load_state(blob)
         a = torch.from_numpy(acts[t])
         mode = (t + n_scen) % 3
         ref = orc.step(acts[t])
